@@ -1,0 +1,147 @@
+/* b200fwd -- C ABI of the B200-native forward-pass engine (libb200fwd.so).
+ *
+ * The reference (githubpradeep/llm_np_cp) has no FFI/plugin boundary: its boundary is the Python call
+ * surface  model(input_ids, use_cache, kv_cache) -> (loss, logits, kv_cache, hidden_states, attentions)
+ * (llama3.2_model_numpy.py:777-830) built from a config object + a {hf_name: tensor} dict
+ * (llama3.2_model_numpy.py:1023-1047).  This header is what a binding for that surface needs; the
+ * Python host in llm_np_cp_b200/ re-creates the reference's classes on top of it with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * B2_ERR_* code and leaves a message retrievable with b2_last_error() (thread-local).  The engine owns
+ * all device memory it allocates; caller-provided host buffers are never retained.  One engine per
+ * device; an engine is not thread-safe, different engines may be driven from different host threads
+ * (that is the data-parallel story -- no collective is involved).  "dev" pointers are CUDA device
+ * pointers on the engine's device (e.g. torch tensors' data_ptr()).
+ */
+#ifndef B200FWD_H
+#define B200FWD_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_ARG (-1)      /* bad argument / unsupported shape (the reference raises ValueError) */
+#define B2_ERR_CUDA (-2)     /* CUDA runtime / driver error */
+#define B2_ERR_STATE (-3)    /* call order (e.g. forward before finalize, missing weight) */
+#define B2_ERR_NO_GPU (-4)   /* no usable sm_100 device: there is NO CPU fallback */
+
+#define B2_DTYPE_BF16 0
+#define B2_DTYPE_F32 1
+#define B2_DTYPE_F16 2
+
+#define B2_ACT_SILU 0        /* llama3.2_model_numpy.py:101-105 */
+#define B2_ACT_GELU_TANH 1   /* gemma2_model.py:168-169 */
+
+/* Mirrors the config attributes the reference's constructors read
+ * (llama3.2_model_numpy.py:350-357, :158-159, :523, :595-607; gemma2_model.py:434, :658, :867). */
+typedef struct b2_config {
+  int32_t vocab_size, hidden_size, intermediate_size, num_hidden_layers;
+  int32_t num_attention_heads, num_key_value_heads, head_dim;
+  int32_t max_positions;        /* length of the RoPE table the engine precomputes */
+  float rope_theta, rms_norm_eps;
+  int32_t hidden_act;           /* B2_ACT_* */
+  int32_t gemma;                /* 1: (1+gamma) norms, 4-norm layers, sqrt(H) embedding scale (gemma2_model.py) */
+  float final_logit_softcap;    /* 0 = off; Gemma-2: 30 (gemma2_model.py:867-870) */
+  /* Options the reference does NOT implement; 0 = reference behaviour. */
+  float attn_logit_softcap;     /* HF Gemma-2: 50 */
+  int32_t sliding_window;       /* HF Gemma-2: 4096 on even layers */
+  float attn_scale;             /* 0 = 1/sqrt(head_dim) (what the reference does) */
+  int32_t always_causal;        /* 0 = reference quirk: no mask when q_len <= 2 (llama3.2_model_numpy.py:479) */
+  int32_t precise;              /* reserved: hi/lo split-bf16 parity mode */
+} b2_config;
+
+typedef struct b2_engine b2_engine;
+typedef struct b2_cache b2_cache;
+
+/* thread-local message of the last failing call */
+const char* b2_last_error(void);
+/* number of CUDA devices with compute capability 10.x (0 => every compute call fails with B2_ERR_NO_GPU) */
+int b2_device_count(void);
+
+/* -------- engine lifetime: replaces load_model()'s model construction (llama3.2_model_numpy.py:1030-1047) */
+int b2_engine_create(const b2_config* cfg, int device, b2_engine** out);
+void b2_engine_destroy(b2_engine* e);
+/* Upload one tensor by its HF name (the reference's load_weights(name) seam, :1023-1028).  The engine
+ * converts to bf16, concatenates q/k/v and interleaves gate/up into its fused layouts.  `lm_head.weight`
+ * is aliased to `model.embed_tokens.weight` exactly like the reference (:1025-1026). */
+int b2_load_weight(b2_engine* e, const char* hf_name, const void* host_ptr, const int64_t* shape, int ndim,
+                   int dtype);
+/* Checks that every tensor arrived and builds the fused layouts; must precede b2_forward. */
+int b2_finalize(b2_engine* e);
+
+/* -------- KV cache: replaces KVCache (llama3.2_model_numpy.py:311-340) with a preallocated
+ * [L][2][max_batch][NKV][max_tokens][HD] bf16 buffer (post-RoPE K, un-repeated). */
+int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_cache** out);
+void b2_cache_destroy(b2_cache* c);
+int b2_cache_len(const b2_cache* c);   /* KVCache.num_items() */
+int b2_cache_reset(b2_cache* c);
+/* copy layer `layer`'s K or V ([batch][NKV][len][HD], bf16) to a device buffer -- KVCache.key_cache[i] */
+int b2_cache_read(const b2_cache* c, int layer, int which /*0=K,1=V*/, int batch, void* dev_out);
+
+#define B2_LOGITS_NONE 0
+#define B2_LOGITS_ALL 1    /* [B,S,V] fp32 -- what the reference returns (:811) */
+#define B2_LOGITS_LAST 2   /* [B,V] fp32, last position only -- what generate() consumes (:899) */
+
+/* -------- forward: LlamaForCausalLM_np.__call__ / Gemma2ForCausalLM_np.__call__
+ * ids_dev     int64 [B,S] on the device
+ * cache       NULL => use_cache=False (attention over this call's tokens only); else K/V are appended
+ *             and cache length advances by S.  A multi-token call on a non-empty cache returns
+ *             B2_ERR_ARG like the reference raises (App. B Q4) unless cfg.always_causal is set.
+ * logits_dev  fp32 output per logits_mode (may be NULL with B2_LOGITS_NONE)
+ * hidden_dev  optional fp32 [L+1,B,S,H]: the reference's hidden_states tuple (:693-720) for parity tests
+ * stream      cudaStream_t (NULL = the engine's own stream)                                   */
+int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids_dev, int B, int S, int logits_mode,
+               float* logits_dev, float* hidden_dev, void* stream);
+/* Same call with HOST buffers (pageable or pinned): ids H2D, forward, logits D2H, synchronises. */
+int b2_forward_host(b2_engine* e, b2_cache* cache, const int64_t* ids_host, int B, int S, int logits_mode,
+                    float* logits_host, float* hidden_host);
+/* Replays one-token steps through a captured CUDA graph (decode loop of generate(), :881-909).
+ * 1 = enable (default 0). */
+int b2_set_decode_graph(b2_engine* e, int enable);
+
+/* -------- sampling: min_p_sampling (llama3.2_model_numpy.py:948-961) on the device.
+ * logits_dev [B,ld] fp32; u_dev [B] uniforms in [0,1); out_ids_dev int64 [B];
+ * probs_dev optional [B,V] fp32 receives the renormalised distribution (testable part). */
+int b2_sample_min_p(b2_engine* e, const float* logits_dev, int B, int ld, float p_base, const float* u_dev,
+                    int64_t* out_ids_dev, float* probs_dev, void* stream);
+
+/* -------- instrumentation */
+typedef struct b2_stats {
+  int64_t launches;        /* kernels launched by this library since the last reset */
+  int64_t gemm_launches;   /* of which tcgen05 GEMMs */
+  double gemm_ms;          /* device time of the GEMM launches (CUDA events), only while timing is on */
+  double gemm_flops;       /* algorithmic FLOPs of those launches */
+  double attn_ms;
+  double attn_flops;
+  int64_t attn_launches;
+} b2_stats;
+int b2_set_timing(b2_engine* e, int on);          /* record CUDA events around GEMM / attention launches */
+int b2_get_stats(b2_engine* e, b2_stats* out);    /* synchronises the engine stream when timing is on */
+int b2_reset_stats(b2_engine* e);
+
+/* -------- single-kernel entry points (per-kernel parity tests call these through the same ABI) */
+int b2_op_rmsnorm(const float* x_dev, const float* g_dev, void* out_bf16_dev, float* out_f32_dev, int M, int H,
+                  float eps, void* stream);
+int b2_op_add_rmsnorm(float* x_dev, const float* y_dev, const float* g_dev, int M, int H, float eps, void* stream);
+/* C = A . W^T with a fused epilogue.  epi: 0 bf16 out, 1 fp32 out (+softcap), 2 fp32 out += (residual),
+ * 4 GLU on a gate/up-interleaved W (out bf16 [M,N/2]).  bn: N-tile (32/64/128/256), split_k >= 1 (epi 2 only). */
+int b2_op_gemm(const void* a_bf16_dev, const void* w_bf16_dev, void* out_dev, int M, int N, int K, int epi,
+               int bn, int split_k, float softcap, int act, void* stream);
+/* fused QKV projection + RoPE + KV append: a [B*S,H] bf16, w [(NH+2NKV)*HD, H] bf16 ->
+ * q [B*S, NH*HD] bf16, k/v caches [B][NKV][Tmax][HD] bf16 written at positions t0..t0+S-1 */
+int b2_op_qkv_rope(const void* a_dev, const void* w_dev, void* q_dev, void* k_cache_dev, void* v_cache_dev, int B,
+                   int S, int H, int NH, int NKV, int HD, int Tmax, int t0, float rope_theta, int bn, void* stream);
+/* attention over caches holding t0+S tokens; q [B*S, NH*HD] bf16 -> out [B*S, NH*HD] bf16.
+ * decode != 0 selects the one-token kernel (requires S == 1). */
+int b2_op_attention(const void* q_dev, const void* k_cache_dev, const void* v_cache_dev, void* out_dev, int B, int S,
+                    int NH, int NKV, int HD, int Tmax, int t0, float scale, float softcap, int causal, int window,
+                    int decode, void* stream);
+/* rows of gate/up interleaved the way b2_op_gemm(epi=4) expects: out[2I,H] from gate[I,H], up[I,H] (host) */
+int b2_interleave_gate_up(const uint16_t* gate, const uint16_t* up, uint16_t* out, int I, int H);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FWD_H */

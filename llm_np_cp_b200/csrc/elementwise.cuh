@@ -1,0 +1,217 @@
+// Memory-bound kernels of the per-layer path: embedding gather, RMSNorm (warp-shuffle reduction),
+// Gemma's post-norm + residual, last-row gather, min-p sampling.  All are HBM-bound: 16-byte
+// vector accesses, one warp per row, fp32 statistics.
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+// x[m, :] = table[ids[m], :] * scale      (llama3.2_model_numpy.py:675; gemma2_model.py:738-739)
+__global__ void __launch_bounds__(256)
+embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ table, float* __restrict__ x,
+             int M, int H, int V, float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  long long id = ids[row];
+  if (id < 0) id = 0;
+  if (id >= V) id = V - 1;   // NumPy would raise IndexError; the host wrapper validates ids
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * H);
+  float4* dst = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H);
+  for (int i = lane; i < H / 8; i += 32) {
+    const uint4 u = __ldg(src + i);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(h2[0]), b = __bfloat1622float2(h2[1]);
+    const float2 c = __bfloat1622float2(h2[2]), d = __bfloat1622float2(h2[3]);
+    dst[2 * i] = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+    dst[2 * i + 1] = make_float4(c.x * scale, c.y * scale, d.x * scale, d.y * scale);
+  }
+}
+
+constexpr int NORM_MAXV = 24;  // float4 per lane: supports H <= 3072
+
+// out = x * 1/sqrt(mean(x^2)+eps) * g   (LlamaRMSNorm_np, llama3.2_model_numpy.py:256-278; g already holds
+// (1 + gamma) for Gemma-2, gemma2_model.py:334).  One warp per row; the row stays in registers between the
+// reduction and the scaling pass.  Writes bf16 (the next GEMM's A operand; optional "lo" plane at
+// +lo_off columns for the precise mode) and/or fp32 (hidden-state capture / final norm).
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
+               int ld_out, int lo_off, float* __restrict__ out_f32, int M, int H, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  const int nv = H >> 7;  // float4 per lane
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * H);
+  float4 v[NORM_MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    if (i < nv) {
+      v[i] = xr[i * 32 + lane];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float rs = 1.0f / sqrtf(ss / static_cast<float>(H) + eps);
+  const float4* gr = reinterpret_cast<const float4*>(g);
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    if (i < nv) {
+      const float4 gg = __ldg(gr + i * 32 + lane);
+      const float4 o = make_float4(v[i].x * rs * gg.x, v[i].y * rs * gg.y, v[i].z * rs * gg.z, v[i].w * rs * gg.w);
+      const int col = (i * 32 + lane) * 4;
+      if (out_bf16) {
+        __nv_bfloat16* d = out_bf16 + static_cast<size_t>(row) * ld_out + col;
+        *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        if (lo_off) {
+          const float lx = o.x - __bfloat162float(__float2bfloat16_rn(o.x));
+          const float ly = o.y - __bfloat162float(__float2bfloat16_rn(o.y));
+          const float lz = o.z - __bfloat162float(__float2bfloat16_rn(o.z));
+          const float lw = o.w - __bfloat162float(__float2bfloat16_rn(o.w));
+          *reinterpret_cast<uint2*>(d + lo_off) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
+        }
+      }
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * H)[i * 32 + lane] = o;
+    }
+  }
+}
+
+// Gemma-2 post-norms: x += rmsnorm(y) * g   (gemma2_model.py:633-637, :641-643)
+__global__ void __launch_bounds__(256)
+add_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g, int M, int H,
+                   float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  const int nv = H >> 7;
+  const float4* yr = reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * H);
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H);
+  float4 v[NORM_MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    if (i < nv) {
+      v[i] = yr[i * 32 + lane];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float rs = 1.0f / sqrtf(ss / static_cast<float>(H) + eps);
+  const float4* gr = reinterpret_cast<const float4*>(g);
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    if (i < nv) {
+      const float4 gg = __ldg(gr + i * 32 + lane);
+      float4 o = xr[i * 32 + lane];
+      o.x += v[i].x * rs * gg.x;
+      o.y += v[i].y * rs * gg.y;
+      o.z += v[i].z * rs * gg.z;
+      o.w += v[i].w * rs * gg.w;
+      xr[i * 32 + lane] = o;
+    }
+  }
+}
+
+// dst[b, :] = src[b*S + S-1, :]  (last position of every sequence; feeds last-token-only logits)
+__global__ void __launch_bounds__(256)
+gather_last_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int S, int H) {
+  const int b = blockIdx.x;
+  const float4* s = reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * S + S - 1) * H);
+  float4* d = reinterpret_cast<float4*>(dst + static_cast<size_t>(b) * H);
+  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) d[i] = s[i];
+}
+
+__global__ void add_scalar_kernel(int* p, int v) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *p += v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// min-p sampling on the device (min_p_sampling, llama3.2_model_numpy.py:948-961):
+//   p = softmax(logits); keep p >= p_base * max(p); renormalise; draw one index.
+// The reference draws with an unseeded torch.multinomial, so parity is distributional; here the draw
+// is an inverse-CDF lookup (in vocabulary order) of a caller-supplied uniform u[b].
+// One CTA (1024 threads) per row.  probs_out (optional) receives the renormalised distribution.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+  if (warp == 0) {
+    r = is_max ? warp_max(r) : warp_sum(r);
+    if (lane == 0) sh[32] = r;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+__global__ void __launch_bounds__(1024)
+min_p_sample_kernel(const float* __restrict__ logits, int ld, int V, float p_base, const float* __restrict__ u,
+                    long long* __restrict__ out_ids, float* __restrict__ probs_out) {
+  __shared__ float sh[33];
+  __shared__ float seg[1024];
+  __shared__ int pick_seg;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + static_cast<size_t>(b) * ld;
+  // contiguous segment per thread so the CDF runs in vocabulary order
+  const int per = (V + blockDim.x - 1) / blockDim.x;
+  const int lo = min(V, tid * per), hi = min(V, lo + per);
+  float mx = -INFINITY;
+  for (int i = lo; i < hi; ++i) mx = fmaxf(mx, x[i]);
+  mx = block_reduce(mx, sh, true);
+  // p_i >= p_base * p_max  <=>  x_i >= mx + log(p_base)
+  const float thr = mx + logf(p_base);
+  float s = 0.f;
+  for (int i = lo; i < hi; ++i) {
+    const float xi = x[i];
+    if (xi >= thr) s += expf(xi - mx);
+  }
+  seg[tid] = s;
+  const float total = block_reduce(s, sh, false);
+  if (probs_out) {
+    float* po = probs_out + static_cast<size_t>(b) * V;
+    for (int i = lo; i < hi; ++i) {
+      const float xi = x[i];
+      po[i] = (xi >= thr) ? expf(xi - mx) / total : 0.f;
+    }
+  }
+  __syncthreads();
+  const float target = u[b] * total;
+  if (tid == 0) {
+    float c = 0.f;
+    int sgm = blockDim.x - 1;
+    for (int t = 0; t < static_cast<int>(blockDim.x); ++t) {
+      if (c + seg[t] > target) {
+        sgm = t;
+        break;
+      }
+      c += seg[t];
+    }
+    // fall back to the last non-empty segment on round-off
+    while (sgm > 0 && seg[sgm] == 0.f) --sgm;
+    pick_seg = sgm;
+    seg[0] = c;  // cumulative mass before the picked segment (seg[0] no longer needed)
+  }
+  __syncthreads();
+  if (tid == pick_seg) {
+    float c = (tid == 0) ? 0.f : seg[0];
+    if (tid == 0) c = 0.f;
+    int pick = -1, last_kept = -1;
+    for (int i = lo; i < hi; ++i) {
+      const float xi = x[i];
+      if (xi >= thr) {
+        last_kept = i;
+        c += expf(xi - mx);
+        if (c > target) {
+          pick = i;
+          break;
+        }
+      }
+    }
+    out_ids[b] = pick >= 0 ? pick : last_kept;
+  }
+}
+
+}  // namespace b2

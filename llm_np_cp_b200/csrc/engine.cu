@@ -1,0 +1,1067 @@
+// libb200fwd.so -- C ABI (include/b200fwd.h) over the hand-written sm_100a kernels.
+// Host side only orchestrates: device memory, TMA descriptors, launch order, CUDA graph for decode.
+// There is no CPU compute path: without an sm_100 device every compute call fails with B2_ERR_NO_GPU.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/b200fwd.h"
+#include "attention_tcgen05.cuh"
+#include "elementwise.cuh"
+#include "gemm_tcgen05.cuh"
+
+using namespace b2;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CKR(call)            \
+  do {                       \
+    int _r = (call);         \
+    if (_r != B2_OK) return _r; \
+  } while (0)
+
+extern "C" const char* b2_last_error(void) { return g_err; }
+
+extern "C" int b2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+static int require_gpu(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(B2_ERR_NO_GPU, "no CUDA device: libb200fwd has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(B2_ERR_ARG, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return fail(B2_ERR_NO_GPU, "device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous), box = {64 columns (128 B), box_rows}, 128B swizzle
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                     uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u ptr=%p",
+                static_cast<int>(r), (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems,
+                box_rows, ptr);
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+struct Stats {
+  int64_t launches = 0, gemm_launches = 0, attn_launches = 0;
+  bool timing = false;
+  struct Ev {
+    cudaEvent_t a, b;
+    double flops;
+    int kind;
+  };
+  std::vector<Ev> used;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+};
+
+static int g_num_sms[16] = {0};
+static int num_sms() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && g_num_sms[dev]) return g_num_sms[dev];
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (dev < 16) g_num_sms[dev] = n;
+  return n;
+}
+
+template <int BN, int EPI>
+static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  static bool attr[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || !attr[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+    if (dev < 16) attr[dev] = true;
+  }
+  const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM, n_blocks = (p.N + BN - 1) / BN;
+  const int total = m_blocks * n_blocks * p.split_k;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+
+static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t st) {
+  if (p.K % GEMM_BK != 0 || p.K <= 0) return fail(B2_ERR_ARG, "GEMM K=%d must be a positive multiple of 64", p.K);
+  if (p.N % 32 != 0) return fail(B2_ERR_ARG, "GEMM N=%d must be a multiple of 32", p.N);
+  if (epi == EPI_GLU && p.N % 64 != 0) return fail(B2_ERR_ARG, "GLU GEMM N=%d must be a multiple of 64", p.N);
+  if (p.split_k < 1 || (p.K / GEMM_BK) % p.split_k != 0)
+    return fail(B2_ERR_ARG, "split_k=%d must divide K/64=%d", p.split_k, p.K / GEMM_BK);
+  if (p.split_k > 1 && epi != EPI_RESID) return fail(B2_ERR_ARG, "split_k needs the residual epilogue");
+#define GEMM_CASE(BN_, EPI_) \
+  if (bn == BN_ && epi == EPI_) return launch_gemm_t<BN_, EPI_>(ta, tb, p, st)
+  GEMM_CASE(256, EPI_BF16);
+  GEMM_CASE(256, EPI_F32);
+  GEMM_CASE(256, EPI_RESID);
+  GEMM_CASE(256, EPI_QKV_ROPE);
+  GEMM_CASE(256, EPI_GLU);
+  GEMM_CASE(128, EPI_BF16);
+  GEMM_CASE(128, EPI_F32);
+  GEMM_CASE(128, EPI_RESID);
+  GEMM_CASE(128, EPI_QKV_ROPE);
+  GEMM_CASE(128, EPI_GLU);
+  GEMM_CASE(64, EPI_BF16);
+  GEMM_CASE(64, EPI_F32);
+  GEMM_CASE(64, EPI_RESID);
+  GEMM_CASE(64, EPI_QKV_ROPE);
+  GEMM_CASE(64, EPI_GLU);
+  GEMM_CASE(32, EPI_RESID);
+  GEMM_CASE(32, EPI_F32);
+#undef GEMM_CASE
+  return fail(B2_ERR_ARG, "no GEMM instantiation for bn=%d epi=%d", bn, epi);
+}
+
+template <int HD>
+static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                         cudaStream_t st) {
+  auto kern = attn_prefill_kernel<HD>;
+  static bool attr[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || !attr[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<HD>::SMEM_BYTES));
+    if (dev < 16) attr[dev] = true;
+  }
+  dim3 grid((p.S + ATT_BM - 1) / ATT_BM, p.NH, p.B);
+  kern<<<grid, ATT_THREADS, AttnCfg<HD>::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+
+static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, const AttnParams& p_in, int HD,
+                        cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  AttnParams p = p_in;
+  if (const char* ev = getenv("B2_V_LBO")) p.v_lbo = atoi(ev);   // bring-up knobs for the MN-major V descriptor
+  if (const char* ev = getenv("B2_V_SBO")) p.v_sbo = atoi(ev);
+  const uint64_t kv_rows = static_cast<uint64_t>(p.B) * p.NKV * p.Tmax;
+  const int bnkv = HD <= 128 ? 128 : 64;
+  CKR(make_tmap(&tq, q, static_cast<uint64_t>(p.B) * p.S, static_cast<uint64_t>(p.NH) * HD, ldq, ATT_BM));
+  CKR(make_tmap(&tk, kc, kv_rows, HD, HD, bnkv));
+  CKR(make_tmap(&tv, vc, kv_rows, HD, HD, bnkv));
+  if (HD == 64) return launch_attn_t<64>(tq, tk, tv, p, st);
+  if (HD == 128) return launch_attn_t<128>(tq, tk, tv, p, st);
+  if (HD == 256) return launch_attn_t<256>(tq, tk, tv, p, st);
+  return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", HD);
+}
+
+static int attn_decode(const bf16* q, int ldq, const bf16* kc, const bf16* vc, bf16* out, int ldo, int B, int NH,
+                       int NKV, int HD, int Tmax, const int* t0_ptr, float scale, float softcap, int window,
+                       cudaStream_t st) {
+  const int grid = (B * NH + 3) / 4;
+#define DEC(HD_)                                                                                              \
+  if (HD == HD_) {                                                                                            \
+    attn_decode_kernel<HD_><<<grid, 128, 0, st>>>(q, ldq, kc, vc, out, ldo, B, NH, NKV, Tmax, t0_ptr, scale, \
+                                                  softcap, window);                                           \
+    CK(cudaGetLastError());                                                                                   \
+    return B2_OK;                                                                                             \
+  }
+  DEC(64) DEC(128) DEC(256)
+#undef DEC
+  return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", HD);
+}
+
+// host-side RoPE tables mirroring the reference's fp32 arithmetic (llama3.2_model_numpy.py:42-60):
+// inv_freq = 1/(base^(2i/HD)) in fp32, angle = inv_freq*pos in fp32, cos/sin of that fp32 angle.
+static void rope_tables_host(int HD, float base, int max_pos, std::vector<float>& c, std::vector<float>& s) {
+  const int half = HD / 2;
+  std::vector<float> inv(half);
+  for (int i = 0; i < half; ++i) {
+    const float e = static_cast<float>(2 * i) / static_cast<float>(HD);
+    inv[i] = 1.0f / powf(base, e);
+  }
+  c.resize(static_cast<size_t>(max_pos) * half);
+  s.resize(c.size());
+  for (int p = 0; p < max_pos; ++p)
+    for (int i = 0; i < half; ++i) {
+      const float ang = inv[i] * static_cast<float>(p);
+      c[static_cast<size_t>(p) * half + i] = static_cast<float>(cos(static_cast<double>(ang)));
+      s[static_cast<size_t>(p) * half + i] = static_cast<float>(sin(static_cast<double>(ang)));
+    }
+}
+
+static uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ff;
+  uint32_t u;
+  if (exp == 0) {
+    if (man == 0) u = sign;
+    else {
+      int e = -1;
+      uint32_t m = man;
+      do { ++e; m <<= 1; } while (!(m & 0x400));
+      u = sign | ((127 - 15 - e) << 23) | ((m & 0x3ff) << 13);
+    }
+  } else if (exp == 31) u = sign | 0x7f800000u | (man << 13);
+  else u = sign | ((exp - 15 + 127) << 23) | (man << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// ------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------
+struct Layer {
+  bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wd = nullptr;
+  float *g_in = nullptr, *g_post_attn = nullptr, *g_pre_ffn = nullptr, *g_post_ffn = nullptr;
+  unsigned loaded = 0;  // bit per tensor
+};
+
+struct b2_cache {
+  b2_engine* e;
+  int max_batch, max_tokens, len;
+  bf16* kv;      // [L][2][max_batch][NKV][max_tokens][HD]
+  int* t0_dev;
+  size_t plane;  // elements per (layer, k|v)
+};
+
+struct GraphKey {
+  const void *ids, *logits, *cache;
+  int B, mode;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(ids, logits, cache, B, mode) < std::tie(o.ids, o.logits, o.cache, o.B, o.mode);
+  }
+};
+
+struct b2_engine {
+  b2_config cfg;
+  int device;
+  cudaStream_t stream;
+  bool finalized = false;
+  int q_cols, kv_cols, qkv_n;
+  bf16* embed = nullptr;
+  float* g_final = nullptr;
+  bool embed_loaded = false, final_loaded = false;
+  std::vector<Layer> layers;
+  float *rope_cos = nullptr, *rope_sin = nullptr;
+  // workspace
+  int ws_tokens = 0, ws_batch = 0;
+  float *x = nullptr, *y = nullptr, *xl = nullptr;
+  bf16 *xn = nullptr, *q = nullptr, *att = nullptr, *hb = nullptr, *xnl = nullptr;
+  int64_t* ids_ws = nullptr;
+  float* logits_ws = nullptr;
+  size_t logits_ws_elems = 0;
+  b2_cache* scratch = nullptr;  // used when the caller passes no cache (use_cache=False)
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
+  Stats st;
+  bool decode_graph = false;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  bool capturing = false;
+};
+
+static int get_tmap(b2_engine* e, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    const CUtensorMap** out) {
+  auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+  auto it = e->tmaps.find(key);
+  if (it == e->tmaps.end()) {
+    CUtensorMap m;
+    CKR(make_tmap(&m, ptr, rows, cols, ld, box_rows));
+    it = e->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return B2_OK;
+}
+
+static void time_begin(b2_engine* e, cudaStream_t st, double flops, int kind) {
+  if (!e->st.timing || e->capturing) return;
+  Stats::Ev ev;
+  if (!e->st.pool.empty()) {
+    ev.a = e->st.pool.back().first;
+    ev.b = e->st.pool.back().second;
+    e->st.pool.pop_back();
+  } else {
+    cudaEventCreate(&ev.a);
+    cudaEventCreate(&ev.b);
+  }
+  ev.flops = flops;
+  ev.kind = kind;
+  cudaEventRecord(ev.a, st);
+  e->st.used.push_back(ev);
+}
+static void time_end(b2_engine* e, cudaStream_t st) {
+  if (!e->st.timing || e->capturing) return;
+  cudaEventRecord(e->st.used.back().b, st);
+}
+
+// C = A . W^T through the engine (cached descriptors, stats)
+static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* a, int lda, const bf16* w, GemmParams p) {
+  const CUtensorMap *ta, *tb;
+  CKR(get_tmap(e, a, e->ws_tokens > p.M ? e->ws_tokens : p.M, p.K, lda, GEMM_BM, &ta));
+  CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, bn, &tb));
+  time_begin(e, st, 2.0 * p.M * static_cast<double>(p.N) * p.K, 0);
+  int r = launch_gemm(bn, epi, *ta, *tb, p, st);
+  time_end(e, st);
+  e->st.launches++;
+  e->st.gemm_launches++;
+  return r;
+}
+
+extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** out) {
+  if (!cfg || !out) return fail(B2_ERR_ARG, "null argument");
+  CKR(require_gpu(device));
+  const b2_config& c = *cfg;
+  if (c.hidden_size % 128 || c.hidden_size > 128 * NORM_MAXV)
+    return fail(B2_ERR_ARG, "hidden_size %d must be a multiple of 128 and <= %d", c.hidden_size, 128 * NORM_MAXV);
+  if (c.head_dim != 64 && c.head_dim != 128 && c.head_dim != 256)
+    return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", c.head_dim);
+  if (c.num_key_value_heads <= 0 || c.num_attention_heads % c.num_key_value_heads)
+    return fail(B2_ERR_ARG, "num_attention_heads %d must be a multiple of num_key_value_heads %d",
+                c.num_attention_heads, c.num_key_value_heads);
+  // the reference raises ValueError on the same condition (llama3.2_model_numpy.py:361-365)
+  if (c.hidden_size % c.num_attention_heads)
+    return fail(B2_ERR_ARG, "hidden_size must be divisible by num_heads (got `hidden_size`: %d and `num_heads`: %d).",
+                c.hidden_size, c.num_attention_heads);
+  if (c.intermediate_size % 64) return fail(B2_ERR_ARG, "intermediate_size %d must be a multiple of 64", c.intermediate_size);
+  if (c.vocab_size % 32) return fail(B2_ERR_ARG, "vocab_size %d must be a multiple of 32", c.vocab_size);
+  if (c.max_positions <= 0) return fail(B2_ERR_ARG, "max_positions must be positive");
+  CK(cudaSetDevice(device));
+  b2_engine* e = new b2_engine();
+  e->cfg = c;
+  e->device = device;
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->q_cols = c.num_attention_heads * c.head_dim;
+  e->kv_cols = c.num_key_value_heads * c.head_dim;
+  e->qkv_n = e->q_cols + 2 * e->kv_cols;
+  if (e->qkv_n % 32) return fail(B2_ERR_ARG, "fused QKV width %d must be a multiple of 32", e->qkv_n);
+  const size_t H = c.hidden_size, I = c.intermediate_size;
+  CK(cudaMalloc(&e->embed, static_cast<size_t>(c.vocab_size) * H * 2));
+  CK(cudaMalloc(&e->g_final, H * 4));
+  e->layers.resize(c.num_hidden_layers);
+  for (auto& L : e->layers) {
+    CK(cudaMalloc(&L.wqkv, static_cast<size_t>(e->qkv_n) * H * 2));
+    CK(cudaMalloc(&L.wo, H * e->q_cols * 2));
+    CK(cudaMalloc(&L.wgu, 2 * I * H * 2));
+    CK(cudaMalloc(&L.wd, H * I * 2));
+    CK(cudaMalloc(&L.g_in, H * 4));
+    CK(cudaMalloc(&L.g_post_attn, H * 4));
+    if (c.gemma) {
+      CK(cudaMalloc(&L.g_pre_ffn, H * 4));
+      CK(cudaMalloc(&L.g_post_ffn, H * 4));
+    }
+  }
+  std::vector<float> cs, sn;
+  rope_tables_host(c.head_dim, c.rope_theta, c.max_positions, cs, sn);
+  CK(cudaMalloc(&e->rope_cos, cs.size() * 4));
+  CK(cudaMalloc(&e->rope_sin, sn.size() * 4));
+  CK(cudaMemcpy(e->rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+  *out = e;
+  return B2_OK;
+}
+
+static void free_ws(b2_engine* e) {
+  cudaFree(e->x); cudaFree(e->y); cudaFree(e->xl); cudaFree(e->xn); cudaFree(e->q); cudaFree(e->att);
+  cudaFree(e->hb); cudaFree(e->xnl); cudaFree(e->ids_ws);
+  e->x = e->y = e->xl = nullptr;
+  e->xn = e->q = e->att = e->hb = e->xnl = nullptr;
+  e->ids_ws = nullptr;
+  e->tmaps.clear();
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+  e->graphs.clear();
+}
+
+extern "C" void b2_cache_destroy(b2_cache* c) {
+  if (!c) return;
+  cudaFree(c->kv);
+  cudaFree(c->t0_dev);
+  delete c;
+}
+
+extern "C" void b2_engine_destroy(b2_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  free_ws(e);
+  if (e->scratch) b2_cache_destroy(e->scratch);
+  cudaFree(e->logits_ws);
+  cudaFree(e->embed); cudaFree(e->g_final); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
+  for (auto& L : e->layers) {
+    cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd);
+    cudaFree(L.g_in); cudaFree(L.g_post_attn); cudaFree(L.g_pre_ffn); cudaFree(L.g_post_ffn);
+  }
+  for (auto& ev : e->st.used) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  for (auto& ev : e->st.pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+// convert a host tensor to bf16 bits
+static void to_bf16_host(const void* src, size_t n, int dtype, std::vector<uint16_t>& out) {
+  out.resize(n);
+  if (dtype == B2_DTYPE_BF16) memcpy(out.data(), src, n * 2);
+  else if (dtype == B2_DTYPE_F32) {
+    const float* f = static_cast<const float*>(src);
+    for (size_t i = 0; i < n; ++i) out[i] = f32_to_bf16(f[i]);
+  } else {
+    const uint16_t* h = static_cast<const uint16_t*>(src);
+    for (size_t i = 0; i < n; ++i) out[i] = f32_to_bf16(f16_to_f32(h[i]));
+  }
+}
+static void to_f32_host(const void* src, size_t n, int dtype, float add, std::vector<float>& out) {
+  out.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    float v;
+    if (dtype == B2_DTYPE_F32) v = static_cast<const float*>(src)[i];
+    else if (dtype == B2_DTYPE_BF16) {
+      uint32_t u = static_cast<uint32_t>(static_cast<const uint16_t*>(src)[i]) << 16;
+      memcpy(&v, &u, 4);
+    } else v = f16_to_f32(static_cast<const uint16_t*>(src)[i]);
+    out[i] = v + add;
+  }
+}
+
+enum { T_IN = 1, T_Q = 2, T_K = 4, T_V = 8, T_O = 16, T_POST = 32, T_GATE = 64, T_UP = 128, T_DOWN = 256,
+       T_PRE_FFN = 512, T_POST_FFN = 1024 };
+
+extern "C" int b2_load_weight(b2_engine* e, const char* name, const void* host, const int64_t* shape, int ndim,
+                              int dtype) {
+  if (!e || !name || !host || !shape) return fail(B2_ERR_ARG, "null argument");
+  if (dtype < 0 || dtype > 2) return fail(B2_ERR_ARG, "unknown dtype %d", dtype);
+  CK(cudaSetDevice(e->device));
+  const b2_config& c = e->cfg;
+  const int64_t H = c.hidden_size, I = c.intermediate_size;
+  std::string n(name);
+  auto want = [&](int64_t r, int64_t cc) -> int {
+    if (cc == 0) {
+      if (ndim != 1 || shape[0] != r) return fail(B2_ERR_ARG, "%s: expected shape [%lld]", name, (long long)r);
+    } else if (ndim != 2 || shape[0] != r || shape[1] != cc)
+      return fail(B2_ERR_ARG, "%s: expected shape [%lld,%lld]", name, (long long)r, (long long)cc);
+    return B2_OK;
+  };
+  std::vector<uint16_t> hb;
+  std::vector<float> hf;
+  const float gadd = c.gemma ? 1.0f : 0.0f;  // Gemma2RMSNorm_np: weight = gamma + 1 (gemma2_model.py:334)
+  if (n == "lm_head.weight") return B2_OK;   // aliased to the embedding, like the reference (:1025-1026)
+  if (n == "model.embed_tokens.weight") {
+    CKR(want(c.vocab_size, H));
+    to_bf16_host(host, static_cast<size_t>(c.vocab_size) * H, dtype, hb);
+    CK(cudaMemcpy(e->embed, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+    e->embed_loaded = true;
+    return B2_OK;
+  }
+  if (n == "model.norm.weight") {
+    CKR(want(H, 0));
+    to_f32_host(host, H, dtype, gadd, hf);
+    CK(cudaMemcpy(e->g_final, hf.data(), H * 4, cudaMemcpyHostToDevice));
+    e->final_loaded = true;
+    return B2_OK;
+  }
+  int li = -1, off = 0;
+  if (sscanf(name, "model.layers.%d.%n", &li, &off) < 1 || off == 0 || li < 0 || li >= c.num_hidden_layers)
+    return fail(B2_ERR_ARG, "unknown tensor name %s", name);
+  Layer& L = e->layers[li];
+  std::string t(name + off);
+  auto norm = [&](float* dst, unsigned bit) -> int {
+    CKR(want(H, 0));
+    to_f32_host(host, H, dtype, gadd, hf);
+    CK(cudaMemcpy(dst, hf.data(), H * 4, cudaMemcpyHostToDevice));
+    L.loaded |= bit;
+    return B2_OK;
+  };
+  auto mat = [&](bf16* dst, int64_t r, int64_t cc, unsigned bit) -> int {
+    CKR(want(r, cc));
+    to_bf16_host(host, static_cast<size_t>(r) * cc, dtype, hb);
+    CK(cudaMemcpy(dst, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+    L.loaded |= bit;
+    return B2_OK;
+  };
+  auto glu = [&](int which, unsigned bit) -> int {  // 32-row groups: [gate g | up g]
+    CKR(want(I, H));
+    to_bf16_host(host, static_cast<size_t>(I) * H, dtype, hb);
+    const size_t grp = 32 * H * 2;
+    CK(cudaMemcpy2D(reinterpret_cast<uint8_t*>(L.wgu) + which * grp, 2 * grp, hb.data(), grp, grp, I / 32,
+                    cudaMemcpyHostToDevice));
+    L.loaded |= bit;
+    return B2_OK;
+  };
+  if (t == "input_layernorm.weight") return norm(L.g_in, T_IN);
+  if (t == "post_attention_layernorm.weight") return norm(L.g_post_attn, T_POST);
+  if (t == "pre_feedforward_layernorm.weight" && c.gemma) return norm(L.g_pre_ffn, T_PRE_FFN);
+  if (t == "post_feedforward_layernorm.weight" && c.gemma) return norm(L.g_post_ffn, T_POST_FFN);
+  if (t == "self_attn.q_proj.weight") return mat(L.wqkv, e->q_cols, H, T_Q);
+  if (t == "self_attn.k_proj.weight") return mat(L.wqkv + static_cast<size_t>(e->q_cols) * H, e->kv_cols, H, T_K);
+  if (t == "self_attn.v_proj.weight")
+    return mat(L.wqkv + static_cast<size_t>(e->q_cols + e->kv_cols) * H, e->kv_cols, H, T_V);
+  if (t == "self_attn.o_proj.weight") return mat(L.wo, H, e->q_cols, T_O);
+  if (t == "mlp.gate_proj.weight") return glu(0, T_GATE);
+  if (t == "mlp.up_proj.weight") return glu(1, T_UP);
+  if (t == "mlp.down_proj.weight") return mat(L.wd, H, I, T_DOWN);
+  return fail(B2_ERR_ARG, "unknown tensor name %s", name);
+}
+
+extern "C" int b2_finalize(b2_engine* e) {
+  if (!e) return fail(B2_ERR_ARG, "null engine");
+  if (!e->embed_loaded) return fail(B2_ERR_STATE, "missing tensor model.embed_tokens.weight");
+  if (!e->final_loaded) return fail(B2_ERR_STATE, "missing tensor model.norm.weight");
+  unsigned need = T_IN | T_Q | T_K | T_V | T_O | T_POST | T_GATE | T_UP | T_DOWN;
+  if (e->cfg.gemma) need |= T_PRE_FFN | T_POST_FFN;
+  for (size_t i = 0; i < e->layers.size(); ++i)
+    if ((e->layers[i].loaded & need) != need)
+      return fail(B2_ERR_STATE, "layer %zu is missing tensors (have mask 0x%x, need 0x%x)", i, e->layers[i].loaded, need);
+  e->finalized = true;
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// cache
+// ------------------------------------------------------------------------------------------
+extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_cache** out) {
+  if (!e || !out || max_batch <= 0 || max_tokens <= 0) return fail(B2_ERR_ARG, "bad cache arguments");
+  if (max_tokens > e->cfg.max_positions)
+    return fail(B2_ERR_ARG, "cache max_tokens %d exceeds the engine's RoPE table (%d positions)", max_tokens, e->cfg.max_positions);
+  CK(cudaSetDevice(e->device));
+  b2_cache* c = new b2_cache();
+  c->e = e;
+  c->max_batch = max_batch;
+  c->max_tokens = max_tokens;
+  c->len = 0;
+  c->plane = static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * max_tokens * e->cfg.head_dim;
+  const size_t bytes = c->plane * 2 * e->cfg.num_hidden_layers * 2;
+  CK(cudaMalloc(&c->kv, bytes));
+  CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
+  CK(cudaMalloc(&c->t0_dev, 4));
+  CK(cudaMemset(c->t0_dev, 0, 4));
+  *out = c;
+  return B2_OK;
+}
+extern "C" int b2_cache_len(const b2_cache* c) { return c ? c->len : fail(B2_ERR_ARG, "null cache"); }
+extern "C" int b2_cache_reset(b2_cache* c) {
+  if (!c) return fail(B2_ERR_ARG, "null cache");
+  CK(cudaSetDevice(c->e->device));
+  CK(cudaStreamSynchronize(c->e->stream));
+  c->len = 0;
+  CK(cudaMemset(c->t0_dev, 0, 4));
+  return B2_OK;
+}
+static bf16* cache_k(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2) * c->plane; }
+static bf16* cache_v(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2 + 1) * c->plane; }
+
+extern "C" int b2_cache_read(const b2_cache* c, int layer, int which, int batch, void* dev_out) {
+  if (!c || !dev_out || layer < 0 || layer >= c->e->cfg.num_hidden_layers || batch <= 0 || batch > c->max_batch)
+    return fail(B2_ERR_ARG, "bad cache_read arguments");
+  const b2_config& g = c->e->cfg;
+  CK(cudaSetDevice(c->e->device));
+  const bf16* src = which ? cache_v(c, layer) : cache_k(c, layer);
+  // [batch*NKV] slabs of [len, HD] out of [max_tokens, HD]
+  CK(cudaMemcpy2DAsync(dev_out, static_cast<size_t>(c->len) * g.head_dim * 2, src,
+                       static_cast<size_t>(c->max_tokens) * g.head_dim * 2, static_cast<size_t>(c->len) * g.head_dim * 2,
+                       static_cast<size_t>(batch) * g.num_key_value_heads, cudaMemcpyDeviceToDevice, c->e->stream));
+  CK(cudaStreamSynchronize(c->e->stream));
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+static int ensure_ws(b2_engine* e, int M, int B) {
+  if (M <= e->ws_tokens && B <= e->ws_batch) return B2_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  free_ws(e);
+  const b2_config& c = e->cfg;
+  const size_t H = c.hidden_size, I = c.intermediate_size;
+  const size_t Mp = M > e->ws_tokens ? M : e->ws_tokens, Bp = B > e->ws_batch ? B : e->ws_batch;
+  CK(cudaMalloc(&e->x, Mp * H * 4));
+  if (c.gemma) CK(cudaMalloc(&e->y, Mp * H * 4));
+  CK(cudaMalloc(&e->xn, Mp * H * 2));
+  CK(cudaMalloc(&e->q, Mp * e->q_cols * 2));
+  CK(cudaMalloc(&e->att, Mp * e->q_cols * 2));
+  CK(cudaMalloc(&e->hb, Mp * I * 2));
+  CK(cudaMalloc(&e->ids_ws, Mp * 8));
+  CK(cudaMalloc(&e->xl, Bp * H * 4));
+  CK(cudaMalloc(&e->xnl, Bp * H * 2));
+  e->ws_tokens = static_cast<int>(Mp);
+  e->ws_batch = static_cast<int>(Bp);
+  return B2_OK;
+}
+
+static int rmsnorm(b2_engine* e, cudaStream_t st, const float* x, const float* g, bf16* ob, float* of, int M) {
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, ob, e->cfg.hidden_size, 0, of, M, e->cfg.hidden_size, e->cfg.rms_norm_eps);
+  CK(cudaGetLastError());
+  e->st.launches++;
+  return B2_OK;
+}
+
+static GemmParams base_params(int M, int N, int K) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.k_wrap = K;
+  p.band_m = 32;
+  p.split_k = 1;
+  return p;
+}
+
+// tile width for a GEMM with M rows: wide tiles for prefill, narrow ones so skinny decode GEMMs spread over SMs
+static int pick_bn(int M, int N, int min_bn) {
+  int bn = 256;
+  if (M <= 128) {
+    bn = 64;
+    if (bn < min_bn) bn = min_bn;
+  }
+  (void)N;
+  return bn;
+}
+
+static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int64_t* ids, int B, int S, int logits_mode,
+                      float* logits, float* hidden) {
+  const b2_config& c = e->cfg;
+  const int M = B * S, H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, HD = c.head_dim;
+  const bool decode = (S == 1);
+  const float escale = c.gemma ? sqrtf(static_cast<float>(H)) : 1.0f;
+  embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(ids), e->embed, e->x, M, H, c.vocab_size, escale);
+  CK(cudaGetLastError());
+  e->st.launches++;
+  const int causal = (c.always_causal || S > 2) ? 1 : 0;   // llama3.2_model_numpy.py:479
+  const float scale = c.attn_scale > 0.f ? c.attn_scale : 1.0f / sqrtf(static_cast<float>(HD));
+  for (int li = 0; li < L; ++li) {
+    Layer& Ly = e->layers[li];
+    if (hidden) CK(cudaMemcpyAsync(hidden + static_cast<size_t>(li) * M * H, e->x, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
+    CKR(rmsnorm(e, st, e->x, Ly.g_in, e->xn, nullptr, M));
+    {  // fused QKV projection + RoPE + KV-cache append
+      GemmParams p = base_params(M, e->qkv_n, H);
+      p.q_cols = e->q_cols;
+      p.kv_cols = e->kv_cols;
+      p.head_dim = HD;
+      p.S = S;
+      p.Tmax = cache->max_tokens;
+      p.nkv = c.num_key_value_heads;
+      p.q_out = e->q;
+      p.ldq = e->q_cols;
+      p.k_cache = cache_k(cache, li);
+      p.v_cache = cache_v(cache, li);
+      p.t0_ptr = cache->t0_dev;
+      p.rope_cos = e->rope_cos;
+      p.rope_sin = e->rope_sin;
+      CKR(eng_gemm(e, st, pick_bn(M, p.N, HD), EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
+    }
+    const int window = (c.sliding_window > 0 && (li % 2 == 0)) ? c.sliding_window : 0;
+    if (decode) {
+      CKR(attn_decode(e->q, e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, e->q_cols, B, c.num_attention_heads,
+                      c.num_key_value_heads, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st));
+      e->st.launches++;
+    } else {
+      AttnParams a;
+      memset(&a, 0, sizeof(a));
+      a.B = B; a.S = S; a.NH = c.num_attention_heads; a.NKV = c.num_key_value_heads; a.Tmax = cache->max_tokens;
+      a.t0_ptr = cache->t0_dev; a.scale = scale; a.softcap = c.attn_logit_softcap; a.causal = causal; a.window = window;
+      a.out = e->att; a.ldo = e->q_cols;
+      const double T = cache->len + S;
+      const double pairs = causal ? (static_cast<double>(S) * (S + 1) / 2 + static_cast<double>(S) * cache->len) : S * T;
+      time_begin(e, st, 4.0 * B * c.num_attention_heads * HD * pairs, 1);
+      int r = attn_prefill(e->q, e->q_cols, cache_k(cache, li), cache_v(cache, li), a, HD, st);
+      time_end(e, st);
+      CKR(r);
+      e->st.launches++;
+      e->st.attn_launches++;
+    }
+    if (!c.gemma) {
+      GemmParams p = base_params(M, H, e->q_cols);
+      p.out = e->x; p.ldo = H;
+      if (M <= 128) p.split_k = (e->q_cols / 64) % 4 == 0 ? 4 : 1;
+      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_RESID, e->att, e->q_cols, Ly.wo, p));   // x += attn . Wo^T
+      CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M));
+    } else {
+      GemmParams p = base_params(M, H, e->q_cols);
+      p.out = e->y; p.ldo = H;
+      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->att, e->q_cols, Ly.wo, p));
+      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, e->y, Ly.g_post_attn, M, H, c.rms_norm_eps);
+      CK(cudaGetLastError());
+      e->st.launches++;
+      CKR(rmsnorm(e, st, e->x, Ly.g_pre_ffn, e->xn, nullptr, M));
+    }
+    {
+      GemmParams p = base_params(M, 2 * I, H);
+      p.out = e->hb; p.ldo = I; p.act = c.hidden_act;
+      CKR(eng_gemm(e, st, pick_bn(M, 2 * I, 0), EPI_GLU, e->xn, H, Ly.wgu, p));           // act(gate)*up
+    }
+    if (!c.gemma) {
+      GemmParams p = base_params(M, H, I);
+      p.out = e->x; p.ldo = H;
+      if (M <= 128) p.split_k = (I / 64) % 4 == 0 ? 4 : 1;
+      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_RESID, e->hb, I, Ly.wd, p));              // x += h . Wd^T
+    } else {
+      GemmParams p = base_params(M, H, I);
+      p.out = e->y; p.ldo = H;
+      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->hb, I, Ly.wd, p));
+      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, e->y, Ly.g_post_ffn, M, H, c.rms_norm_eps);
+      CK(cudaGetLastError());
+      e->st.launches++;
+    }
+  }
+  // final norm + lm_head (tied to the embedding, llama3.2_model_numpy.py:1025-1026)
+  float* hid_last = hidden ? hidden + static_cast<size_t>(L) * M * H : nullptr;
+  if (logits_mode == B2_LOGITS_ALL || hidden) CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, hid_last, M));
+  if (logits_mode == B2_LOGITS_ALL) {
+    GemmParams p = base_params(M, c.vocab_size, H);
+    p.out = logits; p.ldo = c.vocab_size; p.softcap = c.final_logit_softcap;
+    CKR(eng_gemm(e, st, M <= 128 ? 128 : 256, EPI_F32, e->xn, H, e->embed, p));
+  } else if (logits_mode == B2_LOGITS_LAST) {
+    const bf16* a = e->xn;
+    int lda_rows = 0;
+    if (S == 1) {
+      if (!hidden) CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, nullptr, M));
+    } else {
+      gather_last_kernel<<<B, 256, 0, st>>>(e->x, e->xl, B, S, H);
+      CK(cudaGetLastError());
+      e->st.launches++;
+      CKR(rmsnorm(e, st, e->xl, e->g_final, e->xnl, nullptr, B));
+      a = e->xnl;
+      lda_rows = 1;
+    }
+    GemmParams p = base_params(B, c.vocab_size, H);
+    p.out = logits; p.ldo = c.vocab_size; p.softcap = c.final_logit_softcap;
+    const CUtensorMap *ta, *tb;
+    CKR(get_tmap(e, a, lda_rows ? e->ws_batch : e->ws_tokens, H, H, GEMM_BM, &ta));
+    const int bn = B <= 128 ? 128 : 256;
+    CKR(get_tmap(e, e->embed, c.vocab_size, H, H, bn, &tb));
+    time_begin(e, st, 2.0 * B * static_cast<double>(c.vocab_size) * H, 0);
+    int r = launch_gemm(bn, EPI_F32, *ta, *tb, p, st);
+    time_end(e, st);
+    CKR(r);
+    e->st.launches++;
+    e->st.gemm_launches++;
+  }
+  add_scalar_kernel<<<1, 32, 0, st>>>(cache->t0_dev, S);
+  CK(cudaGetLastError());
+  e->st.launches++;
+  return B2_OK;
+}
+
+extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int B, int S, int logits_mode,
+                          float* logits, float* hidden, void* stream) {
+  if (!e || !ids) return fail(B2_ERR_ARG, "null argument");
+  if (!e->finalized) return fail(B2_ERR_STATE, "b2_finalize has not been called");
+  if (B <= 0 || S <= 0) return fail(B2_ERR_ARG, "B and S must be positive");
+  if (logits_mode != B2_LOGITS_NONE && !logits) return fail(B2_ERR_ARG, "logits buffer is null");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+  const b2_config& c = e->cfg;
+  b2_cache* kc = cache;
+  if (!kc) {  // use_cache=False: attention over this call's tokens only
+    if (!e->scratch || e->scratch->max_batch < B || e->scratch->max_tokens < S) {
+      if (e->scratch) { CK(cudaStreamSynchronize(st)); b2_cache_destroy(e->scratch); e->scratch = nullptr; }
+      if (S > c.max_positions) return fail(B2_ERR_ARG, "sequence length %d exceeds max_positions %d", S, c.max_positions);
+      CKR(b2_cache_create(e, B, S, &e->scratch));
+    }
+    kc = e->scratch;
+    kc->len = 0;
+    CK(cudaMemsetAsync(kc->t0_dev, 0, 4, st));
+  } else {
+    if (B > kc->max_batch) return fail(B2_ERR_ARG, "batch %d exceeds the cache's max_batch %d", B, kc->max_batch);
+    if (kc->len + S > kc->max_tokens)
+      return fail(B2_ERR_ARG, "cache overflow: %d cached + %d new > max_tokens %d", kc->len, S, kc->max_tokens);
+    if (kc->len > 0 && S > 1 && !c.always_causal)
+      // the reference's [q,q] mask cannot broadcast onto [q,kv] (llama3.2_model_numpy.py:481-486);
+      // a 2-token chunk is unmasked there (q_len <= 2) and is allowed.
+      if (S > 2)
+        return fail(B2_ERR_ARG, "operands could not be broadcast together: a %d-token call on a non-empty cache (%d items) "
+                                "is not supported by the reference path (set always_causal for chunked prefill)", S, kc->len);
+  }
+  CKR(ensure_ws(e, B * S, B));
+
+  const bool use_graph = e->decode_graph && S == 1 && cache && !hidden && !e->st.timing;
+  if (use_graph) {
+    GraphKey key{ids, logits, cache, B, logits_mode};
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      // warm-up launch outside capture creates every descriptor / function attribute, then restore t0
+      CKR(run_layers(e, kc, st, ids, B, S, logits_mode, logits, nullptr));
+      add_scalar_kernel<<<1, 32, 0, st>>>(kc->t0_dev, -S);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));
+      cudaGraph_t g;
+      e->capturing = true;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int r = run_layers(e, kc, st, ids, B, S, logits_mode, logits, nullptr);
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      e->capturing = false;
+      CKR(r);
+      CK(ce);
+      cudaGraphExec_t ge;
+      CK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      it = e->graphs.emplace(key, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second, st));
+    e->st.launches += 1;
+  } else {
+    CKR(run_layers(e, kc, st, ids, B, S, logits_mode, logits, hidden));
+  }
+  if (cache) cache->len += S;
+  return B2_OK;
+}
+
+extern "C" int b2_forward_host(b2_engine* e, b2_cache* cache, const int64_t* ids_host, int B, int S, int logits_mode,
+                               float* logits_host, float* hidden_host) {
+  if (!e || !ids_host) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(e->device));
+  CKR(ensure_ws(e, B * S, B));
+  const b2_config& c = e->cfg;
+  const size_t M = static_cast<size_t>(B) * S;
+  size_t need = logits_mode == B2_LOGITS_ALL ? M * c.vocab_size : (logits_mode == B2_LOGITS_LAST ? static_cast<size_t>(B) * c.vocab_size : 0);
+  if (need > e->logits_ws_elems) {
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->logits_ws);
+    e->logits_ws = nullptr;
+    CK(cudaMalloc(&e->logits_ws, need * 4));
+    e->logits_ws_elems = need;
+  }
+  float* hidden_dev = nullptr;
+  const size_t hid_elems = static_cast<size_t>(c.num_hidden_layers + 1) * M * c.hidden_size;
+  if (hidden_host) CK(cudaMalloc(&hidden_dev, hid_elems * 4));
+  CK(cudaMemcpyAsync(e->ids_ws, ids_host, M * 8, cudaMemcpyHostToDevice, e->stream));
+  int r = b2_forward(e, cache, e->ids_ws, B, S, logits_mode, e->logits_ws, hidden_dev, e->stream);
+  if (r == B2_OK && need) {
+    cudaError_t ce = cudaMemcpyAsync(logits_host, e->logits_ws, need * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (ce != cudaSuccess) r = fail(B2_ERR_CUDA, "logits D2H failed: %s", cudaGetErrorString(ce));
+  }
+  if (r == B2_OK && hidden_host) {
+    cudaError_t ce = cudaMemcpyAsync(hidden_host, hidden_dev, hid_elems * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (ce != cudaSuccess) r = fail(B2_ERR_CUDA, "hidden D2H failed: %s", cudaGetErrorString(ce));
+  }
+  cudaError_t se = cudaStreamSynchronize(e->stream);
+  if (hidden_dev) cudaFree(hidden_dev);
+  if (r == B2_OK && se != cudaSuccess) r = fail(B2_ERR_CUDA, "forward failed: %s", cudaGetErrorString(se));
+  return r;
+}
+
+extern "C" int b2_set_decode_graph(b2_engine* e, int enable) {
+  if (!e) return fail(B2_ERR_ARG, "null engine");
+  e->decode_graph = enable != 0;
+  return B2_OK;
+}
+
+extern "C" int b2_sample_min_p(b2_engine* e, const float* logits, int B, int ld, float p_base, const float* u,
+                               int64_t* out_ids, float* probs, void* stream) {
+  if (!e || !logits || !u || !out_ids || B <= 0) return fail(B2_ERR_ARG, "bad sample arguments");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+  min_p_sample_kernel<<<B, 1024, 0, st>>>(logits, ld, e->cfg.vocab_size, p_base, u, reinterpret_cast<long long*>(out_ids), probs);
+  CK(cudaGetLastError());
+  e->st.launches++;
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stats
+// ------------------------------------------------------------------------------------------
+extern "C" int b2_set_timing(b2_engine* e, int on) {
+  if (!e) return fail(B2_ERR_ARG, "null engine");
+  e->st.timing = on != 0;
+  return B2_OK;
+}
+extern "C" int b2_reset_stats(b2_engine* e) {
+  if (!e) return fail(B2_ERR_ARG, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  for (auto& ev : e->st.used) e->st.pool.emplace_back(ev.a, ev.b);
+  e->st.used.clear();
+  e->st.launches = e->st.gemm_launches = e->st.attn_launches = 0;
+  return B2_OK;
+}
+extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
+  if (!e || !out) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(e->device));
+  memset(out, 0, sizeof(*out));
+  out->launches = e->st.launches;
+  out->gemm_launches = e->st.gemm_launches;
+  out->attn_launches = e->st.attn_launches;
+  if (!e->st.used.empty()) {
+    CK(cudaDeviceSynchronize());
+    for (auto& ev : e->st.used) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
+      if (ev.kind == 0) { out->gemm_ms += ms; out->gemm_flops += ev.flops; }
+      else { out->attn_ms += ms; out->attn_flops += ev.flops; }
+    }
+  }
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// single-kernel entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int b2_op_rmsnorm(const float* x, const float* g, void* ob, float* of, int M, int H, float eps, void* stream) {
+  CKR(require_gpu(0));
+  if (H % 128 || H > 128 * NORM_MAXV) return fail(B2_ERR_ARG, "H=%d must be a multiple of 128 and <= %d", H, 128 * NORM_MAXV);
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, static_cast<bf16*>(ob), H, 0, of, M, H, eps);
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+extern "C" int b2_op_add_rmsnorm(float* x, const float* y, const float* g, int M, int H, float eps, void* stream) {
+  CKR(require_gpu(0));
+  if (H % 128 || H > 128 * NORM_MAXV) return fail(B2_ERR_ARG, "H=%d must be a multiple of 128 and <= %d", H, 128 * NORM_MAXV);
+  add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, g, M, H, eps);
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" int b2_op_gemm(const void* a, const void* w, void* out, int M, int N, int K, int epi, int bn, int split_k,
+                          float softcap, int act, void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CKR(require_gpu(dev));
+  if (epi == EPI_QKV_ROPE) return fail(B2_ERR_ARG, "use b2_op_qkv_rope");
+  CUtensorMap ta, tb;
+  CKR(make_tmap(&ta, a, M, K, K, GEMM_BM));
+  CKR(make_tmap(&tb, w, N, K, K, bn));
+  GemmParams p = base_params(M, N, K);
+  p.split_k = split_k < 1 ? 1 : split_k;
+  p.out = out;
+  p.ldo = (epi == EPI_GLU) ? N / 2 : N;
+  p.softcap = softcap;
+  p.act = act;
+  return launch_gemm(bn, epi, ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2_op_qkv_rope(const void* a, const void* w, void* q, void* kc, void* vc, int B, int S, int H, int NH,
+                              int NKV, int HD, int Tmax, int t0, float rope_theta, int bn, void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CKR(require_gpu(dev));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int M = B * S, N = (NH + 2 * NKV) * HD;
+  if (bn < HD || bn % HD) return fail(B2_ERR_ARG, "bn=%d must be a multiple of head_dim=%d", bn, HD);
+  std::vector<float> cs, sn;
+  rope_tables_host(HD, rope_theta, Tmax, cs, sn);
+  float *dc = nullptr, *ds = nullptr;
+  int* dt0 = nullptr;
+  CK(cudaMalloc(&dc, cs.size() * 4));
+  CK(cudaMalloc(&ds, sn.size() * 4));
+  CK(cudaMalloc(&dt0, 4));
+  CK(cudaMemcpy(dc, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ds, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dt0, &t0, 4, cudaMemcpyHostToDevice));
+  CUtensorMap ta, tb;
+  CKR(make_tmap(&ta, a, M, H, H, GEMM_BM));
+  CKR(make_tmap(&tb, w, N, H, H, bn));
+  GemmParams p = base_params(M, N, H);
+  p.q_cols = NH * HD; p.kv_cols = NKV * HD; p.head_dim = HD; p.S = S; p.Tmax = Tmax; p.nkv = NKV;
+  p.q_out = static_cast<bf16*>(q); p.ldq = NH * HD;
+  p.k_cache = static_cast<bf16*>(kc); p.v_cache = static_cast<bf16*>(vc);
+  p.t0_ptr = dt0; p.rope_cos = dc; p.rope_sin = ds;
+  int r = launch_gemm(bn, EPI_QKV_ROPE, ta, tb, p, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(dc); cudaFree(ds); cudaFree(dt0);
+  if (r == B2_OK && se != cudaSuccess) return fail(B2_ERR_CUDA, "qkv_rope kernel failed: %s", cudaGetErrorString(se));
+  return r;
+}
+
+extern "C" int b2_op_attention(const void* q, const void* kc, const void* vc, void* out, int B, int S, int NH, int NKV,
+                               int HD, int Tmax, int t0, float scale, float softcap, int causal, int window, int decode,
+                               void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CKR(require_gpu(dev));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* dt0 = nullptr;
+  CK(cudaMalloc(&dt0, 4));
+  CK(cudaMemcpy(dt0, &t0, 4, cudaMemcpyHostToDevice));
+  int r;
+  if (decode) {
+    if (S != 1) { cudaFree(dt0); return fail(B2_ERR_ARG, "decode attention needs S == 1"); }
+    r = attn_decode(static_cast<const bf16*>(q), NH * HD, static_cast<const bf16*>(kc), static_cast<const bf16*>(vc),
+                    static_cast<bf16*>(out), NH * HD, B, NH, NKV, HD, Tmax, dt0, scale, softcap, window, st);
+  } else {
+    AttnParams a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.S = S; a.NH = NH; a.NKV = NKV; a.Tmax = Tmax; a.t0_ptr = dt0; a.scale = scale; a.softcap = softcap;
+    a.causal = causal; a.window = window; a.out = static_cast<bf16*>(out); a.ldo = NH * HD;
+    r = attn_prefill(static_cast<const bf16*>(q), NH * HD, static_cast<const bf16*>(kc), static_cast<const bf16*>(vc), a, HD, st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(dt0);
+  if (r == B2_OK && se != cudaSuccess) return fail(B2_ERR_CUDA, "attention kernel failed: %s", cudaGetErrorString(se));
+  return r;
+}
+
+extern "C" int b2_interleave_gate_up(const uint16_t* gate, const uint16_t* up, uint16_t* out, int I, int H) {
+  if (!gate || !up || !out || I % 32) return fail(B2_ERR_ARG, "bad interleave arguments (I must be a multiple of 32)");
+  const size_t grp = static_cast<size_t>(32) * H;
+  for (int g = 0; g < I / 32; ++g) {
+    memcpy(out + (2 * g) * grp, gate + g * grp, grp * 2);
+    memcpy(out + (2 * g + 1) * grp, up + g * grp, grp * 2);
+  }
+  return B2_OK;
+}

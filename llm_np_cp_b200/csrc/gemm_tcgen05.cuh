@@ -1,0 +1,377 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . W[N,K]^T
+//
+//   A  activations, bf16 row-major (K contiguous)         -> UMMA A operand, K-major
+//   W  weights in HF layout [out_features, in_features]   -> UMMA B operand, K-major
+//   (this is the reference's Linear_np: y = x . W^T, llama3.2_model_numpy.py:124-144)
+//
+// One CTA per SM, 192 threads:
+//   warp 0    TMA producer: cp.async.bulk.tensor 128B-swizzled {64 x 128} A and {64 x BN} W boxes
+//             into a STAGES-deep shared-memory ring, completion on "full" mbarriers
+//   warp 1    MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
+//             TMEM accumulators; tcgen05.commit releases ring slots / publishes the accumulator
+//   warps 2-5 epilogue: tcgen05.ld (lane = output row) -> fused epilogue -> global stores, overlapped
+//             with the next tile's main loop through the double-buffered accumulator
+//
+// Fused epilogues: plain bf16 / fp32 (+tanh soft-cap, gemma2_model.py:867-870),
+// residual add (llama3.2_model_numpy.py:569,578), RoPE + KV-cache append for the fused QKV weight
+// (:459, :464-465), and act(gate)*up for the interleaved gate/up weight (:176-182).
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+enum GemmEpi : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_QKV_ROPE = 3, EPI_GLU = 4 };
+
+struct GemmParams {
+  int M, N, K;   // K = contraction length seen by A (2*k_wrap in hi/lo "precise" mode)
+  int k_wrap;    // W k-coordinate = k % k_wrap
+  int band_m;    // rasterisation: m-blocks per band (W tiles stay hot in L2 inside a band)
+  int split_k;   // >1: K is split across CTAs (skinny decode GEMMs); only EPI_RESID (fp32 atomics) supports it
+  // EPI_BF16 / EPI_F32 / EPI_RESID / EPI_GLU
+  void* out;
+  int ldo;         // row stride of out, in elements
+  float softcap;   // EPI_F32: cap * tanh(x / cap) when > 0
+  int act;         // EPI_GLU: 0 = SiLU, 1 = tanh-GELU
+  int lo_off;      // EPI_GLU/EPI_BF16 precise mode: column offset of the bf16 "lo" plane (0 = none)
+  // EPI_QKV_ROPE
+  int q_cols, kv_cols, head_dim, S, Tmax, nkv;
+  __nv_bfloat16* q_out;
+  int ldq;
+  __nv_bfloat16* k_cache;  // [B][NKV][Tmax][HD] (this layer)
+  __nv_bfloat16* v_cache;
+  const int* t0_ptr;       // device scalar: tokens already in the cache
+  const float* rope_cos;   // [max_pos][HD/2]
+  const float* rope_sin;
+  int kv_lo_off;           // precise mode: element offset of the lo plane of the caches (0 = none)
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+};
+
+__device__ __forceinline__ float act_silu(float g) { return __fdividef(g, 1.0f + __expf(-g)); }
+__device__ __forceinline__ float act_gelu_tanh(float g) {
+  const float k = 0.7978845608028654f;
+  return 0.5f * g * (1.0f + tanhf(k * (g + 0.044715f * g * g * g)));
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    d[i] = u;
+  }
+}
+// residual of a bf16 rounding, itself rounded to bf16 (the "lo" plane of the precise mode)
+__device__ __forceinline__ void split_lo(const float (&v)[32], float (&lo)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) lo[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint32_t tacc, int mb, int nb, int quarter,
+                                              int lane) {
+  const int row = mb * GEMM_BM + quarter * 32 + lane;
+  const bool row_ok = row < p.M;
+  const int col0 = nb * BN;
+  const uint32_t trow = tacc + (static_cast<uint32_t>(quarter * 32) << 16);
+
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col = col0 + c * 32;
+      if (col >= p.N) break;
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+      uint32_t r[32];
+      tmem_ld32(trow + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      if (!row_ok) continue;
+      if constexpr (EPI == EPI_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+        store_bf16x32(o, v);
+        if (p.lo_off) {
+          float lo[32];
+          split_lo(v, lo);
+          store_bf16x32(o + p.lo_off, lo);
+        }
+      } else if constexpr (EPI == EPI_F32) {
+        if (p.softcap > 0.f) {
+          const float inv = 1.0f / p.softcap;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = p.softcap * tanhf(v[i] * inv);
+        }
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) __stcs(o + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+      } else {  // EPI_RESID: x += acc, fp32 residual stream
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
+        if (p.split_k > 1) {
+          float* of = reinterpret_cast<float*>(o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(of + i, v[i]);
+          continue;
+        }
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = o[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x[i].x += v[4 * i];
+          x[i].y += v[4 * i + 1];
+          x[i].z += v[4 * i + 2];
+          x[i].w += v[4 * i + 3];
+          o[i] = x[i];
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_GLU) {
+    // W rows are interleaved in 32-row groups: [gate 32j..32j+31 | up 32j..32j+31] -> column chunk 2j is
+    // gate, chunk 2j+1 is up, output column = N/2-space (col0/2 + 32j).
+#pragma unroll 1
+    for (int j = 0; j < BN / 64; ++j) {
+      const int col = col0 + j * 64;
+      if (col >= p.N) break;
+      __syncwarp();
+      uint32_t g[32], u[32];
+      tmem_ld32(trow + j * 64, g);
+      tmem_ld32(trow + j * 64 + 32, u);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float gv = __uint_as_float(g[i]);
+        const float a = p.act == 0 ? act_silu(gv) : act_gelu_tanh(gv);
+        v[i] = a * __uint_as_float(u[i]);
+      }
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + (col >> 1);
+      store_bf16x32(o, v);
+      if (p.lo_off) {
+        float lo[32];
+        split_lo(v, lo);
+        store_bf16x32(o + p.lo_off, lo);
+      }
+    }
+  } else {  // EPI_QKV_ROPE
+    const int HD = p.head_dim;
+    const int half_chunks = HD >> 6;  // chunks (of 32 columns) per half head
+    const int t0 = *p.t0_ptr;
+    const int b = row / p.S, s = row - b * p.S;
+    const int pos = t0 + s;
+    const float* cosr = p.rope_cos + static_cast<size_t>(pos) * (HD >> 1);
+    const float* sinr = p.rope_sin + static_cast<size_t>(pos) * (HD >> 1);
+#pragma unroll 1
+    for (int hh = 0; hh < BN / HD; ++hh) {
+      const int n0 = col0 + hh * HD;  // first fused-QKV column of this head
+      if (n0 >= p.N) break;
+      __nv_bfloat16* dst;
+      bool rope = true;
+      int lo_off = 0;
+      if (n0 < p.q_cols) {
+        dst = p.q_out + static_cast<size_t>(row) * p.ldq + n0;
+        lo_off = p.lo_off;
+      } else {
+        int n1 = n0 - p.q_cols;
+        __nv_bfloat16* base = p.k_cache;
+        if (n1 >= p.kv_cols) {
+          n1 -= p.kv_cols;
+          base = p.v_cache;
+          rope = false;
+        }
+        const int kvh = n1 / HD;
+        dst = base + (static_cast<size_t>(b * p.nkv + kvh) * p.Tmax + pos) * HD;
+        lo_off = p.kv_lo_off;
+      }
+#pragma unroll 1
+      for (int i = 0; i < half_chunks; ++i) {
+        __syncwarp();
+        uint32_t a[32], c[32];
+        const int cl = hh * (HD >> 5) + i;  // chunk holding x1 (first half of the head)
+        tmem_ld32(trow + cl * 32, a);
+        tmem_ld32(trow + (cl + half_chunks) * 32, c);  // matching x2 chunk (second half)
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float x1[32], x2[32];
+        if (rope) {
+          // q*cos + rotate_half(q)*sin with rotate_half = [-x2, x1]  (llama3.2_model_numpy.py:69-90)
+          const float4* c4 = reinterpret_cast<const float4*>(cosr + i * 32);
+          const float4* s4 = reinterpret_cast<const float4*>(sinr + i * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 cc = __ldg(c4 + j), ss = __ldg(s4 + j);
+            const float cs[4] = {cc.x, cc.y, cc.z, cc.w}, sn[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float p1 = __uint_as_float(a[4 * j + e]), p2 = __uint_as_float(c[4 * j + e]);
+              x1[4 * j + e] = p1 * cs[e] - p2 * sn[e];
+              x2[4 * j + e] = p2 * cs[e] + p1 * sn[e];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x1[j] = __uint_as_float(a[j]);
+            x2[j] = __uint_as_float(c[j]);
+          }
+        }
+        store_bf16x32(dst + i * 32, x1);
+        store_bf16x32(dst + (HD >> 1) + i * 32, x2);
+        if (lo_off) {
+          float lo[32];
+          split_lo(x1, lo);
+          store_bf16x32(dst + lo_off + i * 32, lo);
+          split_lo(x2, lo);
+          store_bf16x32(dst + lo_off + (HD >> 1) + i * 32, lo);
+        }
+      }
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int total = m_blocks * n_blocks * p.split_k;
+  const int KB = (p.K / GEMM_BK) / p.split_k;   // k-blocks per tile
+  const int per_band = p.band_m * n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& mb, int& nb, int& kb0) {
+    kb0 = (tile % p.split_k) * KB;
+    tile /= p.split_k;
+    const int band = tile / per_band, r = tile - band * per_band;
+    const int mrem = m_blocks - band * p.band_m;
+    const int mcnt = mrem < p.band_m ? mrem : p.band_m;
+    nb = r / mcnt;
+    mb = band * p.band_m + (r - nb * mcnt);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int mb, nb, kb0;
+        tile_coords(tile, mb, nb, kb0);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          const int ka = (kb0 + kb) * GEMM_BK;
+          const int kw = ka >= p.k_wrap ? ka - p.k_wrap : ka;
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_a, &full[stage], ka, mb * GEMM_BM, kEvictNormal);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_b, &full[stage], kw, nb * BN, kEvictNormal);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss(d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int mb, nb, kb0;
+      tile_coords(tile, mb, nb, kb0);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      gemm_epilogue<BN, EPI>(p, tmem_base + acc * BN, mb, nb, quarter, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace b2

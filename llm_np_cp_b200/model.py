@@ -1,0 +1,358 @@
+"""Host-side mirror of the reference's Python call surface, driving libb200fwd.so.
+
+Reference surface:
+  tokenizer, model, config = load_model(name)                      llama3.2_model_numpy.py:1030-1047
+  loss, logits, kv_cache, hidden_states, attentions = model(ids, use_cache=..., kv_cache=...)   :777-830
+  text = generate(prompt, tokenizer, model, max_tokens, kv_cache=KVCache(), config=config)     :873-910
+
+Same names, argument meaning and error behaviour; arrays that the reference's CuPy twin keeps on the
+GPU (logits, hidden states, cache contents) are returned as torch CUDA tensors.  Deviations, all
+forced by never materialising [B,NH,S,T] scores: ``attentions`` is None.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B2Config, B2Stats, check
+
+LOGITS_NONE, LOGITS_ALL, LOGITS_LAST = 0, 1, 2
+
+
+class AttributeDict(dict):
+    """dict with attribute access (llama3.2_model_numpy.py:212-215)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+
+# the reference's module-global injection seam (llama3.2_model_numpy.py:1023-1028)
+weights: Dict[str, torch.Tensor] = dict()
+
+
+def load_weights(key):
+    """Name -> tensor lookup with the lm_head alias (llama3.2_model_numpy.py:1024-1028)."""
+    if key == "lm_head.weight":
+        key = "model.embed_tokens.weight"
+    return weights[key]
+
+
+_DTYPES = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}
+
+
+def _cfg_get(config, key, default=None):
+    try:
+        return config[key]
+    except (KeyError, TypeError):
+        return getattr(config, key, default)
+
+
+class KVCache:
+    """KVCache() of the reference (llama3.2_model_numpy.py:311-340) backed by a preallocated device
+    buffer.  ``KVCache()`` takes no arguments there; here capacity is fixed at first use
+    (``max_tokens`` defaults to the model's RoPE-table length capped at 8192)."""
+
+    def __init__(self, max_batch: Optional[int] = None, max_tokens: Optional[int] = None):
+        self.max_batch, self.max_tokens = max_batch, max_tokens
+        self._h = None
+        self._model = None
+
+    def _bind(self, model, batch):
+        if self._h is None:
+            mb = self.max_batch or batch
+            mt = self.max_tokens or min(model._cfg.max_positions, 8192)
+            h = C.c_void_p()
+            check(_lib.lib().b2_cache_create(model._h, mb, mt, C.byref(h)))
+            self._h, self._model, self.max_batch, self.max_tokens = h, model, mb, mt
+        elif self._model is not model:
+            raise ValueError("KVCache is bound to a different model")
+        return self._h
+
+    def num_items(self) -> int:
+        return 0 if self._h is None else int(_lib.lib().b2_cache_len(self._h))
+
+    def reset(self):
+        if self._h is not None:
+            check(_lib.lib().b2_cache_reset(self._h))
+
+    def _read(self, which, batch=None):
+        if self._h is None or self.num_items() == 0:
+            return []
+        m = self._model
+        B = batch or self.max_batch
+        out = []
+        for li in range(m._cfg.num_hidden_layers):
+            t = torch.empty((B, m._cfg.num_key_value_heads, self.num_items(), m._cfg.head_dim),
+                            dtype=torch.bfloat16, device=m.device)
+            check(_lib.lib().b2_cache_read(self._h, li, which, B, t.data_ptr()))
+            out.append(t)
+        return out
+
+    @property
+    def key_cache(self):
+        """list of [B,NKV,T,HD] post-RoPE keys, one per layer (bf16 device tensors)."""
+        return self._read(0)
+
+    @property
+    def value_cache(self):
+        return self._read(1)
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.lib().b2_cache_destroy(self._h)
+        except Exception:
+            pass
+
+
+class _CausalLM:
+    """Common engine wrapper; subclasses set the family."""
+    family = "llama"
+
+    def __init__(self, config, weights_dict: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
+                 max_positions: Optional[int] = None, *, attn_logit_softcapping=None, sliding_window=None,
+                 use_query_pre_attn_scalar: bool = False, always_causal: bool = False):
+        self.config = config
+        L = _lib.lib()
+        if L.b2_device_count() == 0:
+            raise _lib.B2Error("no sm_100 CUDA device: llm_np_cp_b200 has no CPU fallback")
+        gem = self.family == "gemma2"
+        c = B2Config()
+        c.vocab_size = int(config.vocab_size)
+        c.hidden_size = int(config.hidden_size)
+        c.intermediate_size = int(config.intermediate_size)
+        c.num_hidden_layers = int(config.num_hidden_layers)
+        c.num_attention_heads = int(config.num_attention_heads)
+        c.num_key_value_heads = int(config.num_key_value_heads)
+        c.head_dim = int(config.head_dim)                      # must exist in the config (App. B Q7)
+        mp = int(_cfg_get(config, "max_position_embeddings", 8192))
+        c.max_positions = int(max_positions or min(mp, 16384))
+        c.rope_theta = float(config.rope_theta)
+        c.rms_norm_eps = float(config.rms_norm_eps)
+        act = _cfg_get(config, "hidden_act", None) or _cfg_get(config, "hidden_activation", "silu")
+        if act not in ("silu", "gelu_pytorch_tanh"):
+            raise KeyError(act)                                # ACT2FN_np lookup fails the same way (:111-116)
+        c.hidden_act = 0 if act == "silu" else 1
+        c.gemma = 1 if gem else 0
+        cap = _cfg_get(config, "final_logit_softcapping", None) if gem else None
+        c.final_logit_softcap = float(cap) if cap else 0.0
+        # options beyond the reference (off by default = reference behaviour)
+        c.attn_logit_softcap = float(attn_logit_softcapping or 0.0)
+        c.sliding_window = int(sliding_window or 0)
+        c.attn_scale = float(_cfg_get(config, "query_pre_attn_scalar", c.head_dim)) ** -0.5 if use_query_pre_attn_scalar else 0.0
+        c.always_causal = 1 if always_causal else 0
+        c.precise = 0
+        self._cfg = c
+        self.device = torch.device("cuda", device)
+        self.vocab_size = c.vocab_size
+        h = C.c_void_p()
+        check(L.b2_engine_create(C.byref(c), device, C.byref(h)))
+        self._h = h
+        src = weights_dict if weights_dict is not None else weights
+        self._load(src)
+        check(L.b2_finalize(self._h))
+
+    def _load(self, src):
+        L = _lib.lib()
+        for name, t in src.items():
+            if name == "lm_head.weight":
+                continue                                       # tied to the embedding (:1025-1026)
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(t)
+            t = t.detach().cpu().contiguous()
+            if t.dtype not in _DTYPES:
+                t = t.to(torch.float32)
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            check(L.b2_load_weight(self._h, name.encode(), t.data_ptr(), shape, t.dim(), _DTYPES[t.dtype]))
+
+    # ---- the reference's __call__ (llama3.2_model_numpy.py:777-830 / gemma2_model.py:830-886)
+    def __call__(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, labels=None,
+                 use_cache=None, output_attentions=True, output_hidden_states=True, return_dict=True, kv_cache=None,
+                 logits_mode: int = LOGITS_ALL):
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+        if input_ids is None:
+            if inputs_embeds is not None:
+                raise NotImplementedError("inputs_embeds is not supported by the B200 engine")
+            raise ValueError("You have to specify either input_ids or inputs_embeds")
+        use_cache = use_cache if use_cache is not None else _cfg_get(self.config, "use_cache", False)
+        ids = input_ids
+        if isinstance(ids, np.ndarray):
+            ids = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64))
+        ids = torch.as_tensor(ids, dtype=torch.int64)
+        if ids.dim() != 2:
+            raise ValueError("input_ids must be [batch, seq]")
+        if ids.device.type != "cuda":
+            if int(ids.min()) < 0 or int(ids.max()) >= self.vocab_size:
+                raise IndexError("token id out of range")      # NumPy fancy indexing raises the same (:675)
+            ids = ids.to(self.device, non_blocking=True)
+        ids = ids.contiguous()
+        B, S = ids.shape
+        cache_h = None
+        if use_cache and kv_cache is not None:
+            cache_h = kv_cache._bind(self, B)
+        H, V, Lc = self._cfg.hidden_size, self._cfg.vocab_size, self._cfg.num_hidden_layers
+        logits = hidden = None
+        if logits_mode == LOGITS_ALL:
+            logits = torch.empty((B, S, V), dtype=torch.float32, device=self.device)
+        elif logits_mode == LOGITS_LAST:
+            logits = torch.empty((B, V), dtype=torch.float32, device=self.device)
+        if output_hidden_states:
+            hidden = torch.empty((Lc + 1, B, S, H), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(_lib.lib().b2_forward(self._h, cache_h, ids.data_ptr(), B, S, logits_mode,
+                                    logits.data_ptr() if logits is not None else None,
+                                    hidden.data_ptr() if hidden is not None else None, stream))
+        self._keep = ids                                       # keep inputs alive until the stream is done
+        hs = tuple(hidden[i] for i in range(Lc + 1)) if hidden is not None else None
+        return (None, logits, kv_cache, hs, None)
+
+    # ---- instrumentation
+    def set_timing(self, on: bool):
+        check(_lib.lib().b2_set_timing(self._h, 1 if on else 0))
+
+    def set_decode_graph(self, on: bool):
+        check(_lib.lib().b2_set_decode_graph(self._h, 1 if on else 0))
+
+    def reset_stats(self):
+        check(_lib.lib().b2_reset_stats(self._h))
+
+    def stats(self) -> dict:
+        s = B2Stats()
+        check(_lib.lib().b2_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in B2Stats._fields_}
+
+    def forward_host(self, ids_np: np.ndarray, kv_cache: Optional[KVCache] = None, logits_mode: int = LOGITS_LAST,
+                     out: Optional[np.ndarray] = None):
+        """The C-ABI call with HOST buffers (b2_forward_host): ids H2D, forward, logits D2H."""
+        ids_np = np.ascontiguousarray(ids_np, dtype=np.int64)
+        B, S = ids_np.shape
+        V = self._cfg.vocab_size
+        shape = (B, S, V) if logits_mode == LOGITS_ALL else (B, V)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        cache_h = kv_cache._bind(self, B) if kv_cache is not None else None
+        check(_lib.lib().b2_forward_host(self._h, cache_h, ids_np.ctypes.data, B, S, logits_mode, out.ctypes.data, None))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None:
+                _lib.lib().b2_engine_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class LlamaForCausalLM(_CausalLM):
+    """LlamaForCausalLM_np (llama3.2_model_numpy.py:734-830)."""
+    family = "llama"
+
+
+class Gemma2ForCausalLM(_CausalLM):
+    """Gemma2ForCausalLM_np (gemma2_model.py:787-886).  Reference-parity flags by default: no attention
+    soft-cap, no sliding window, 1/sqrt(head_dim) scaling.  ``hf_flags=True``
+    switches on the HF semantics BASELINE.json asks for (soft-cap, sliding window on even layers)."""
+    family = "gemma2"
+
+    def __init__(self, config, weights_dict=None, device: int = 0, max_positions=None, hf_flags: bool = False, **kw):
+        if hf_flags:
+            kw.setdefault("attn_logit_softcapping", _cfg_get(config, "attn_logit_softcapping", 50.0))
+            kw.setdefault("sliding_window", _cfg_get(config, "sliding_window", 4096))
+            kw.setdefault("use_query_pre_attn_scalar", True)
+            kw.setdefault("always_causal", True)
+        super().__init__(config, weights_dict, device, max_positions, **kw)
+
+
+# the reference's class names, for drop-in imports
+LlamaForCausalLM_np = LlamaForCausalLM
+Gemma2ForCausalLM_np = Gemma2ForCausalLM
+
+
+def min_p_sampling(logits, p_base: float = 0.1, generator: Optional[torch.Generator] = None, model=None,
+                   return_probs: bool = False):
+    """min_p_sampling (llama3.2_model_numpy.py:948-961): softmax -> keep p >= p_base*p_max -> renormalise
+    -> draw.  Runs on the device; the reference's draw is an unseeded torch.multinomial, here it is an
+    inverse-CDF lookup of a uniform from ``generator`` (pass a seeded generator for reproducibility)."""
+    if model is None:
+        raise ValueError("min_p_sampling needs the model (engine handle) that produced the logits")
+    lg = torch.as_tensor(logits, dtype=torch.float32, device=model.device)
+    one = lg.dim() == 1
+    if one:
+        lg = lg[None]
+    lg = lg.contiguous()
+    B, V = lg.shape
+    u = torch.rand(B, generator=generator, dtype=torch.float32).to(model.device)
+    out = torch.empty(B, dtype=torch.int64, device=model.device)
+    probs = torch.empty((B, V), dtype=torch.float32, device=model.device) if return_probs else None
+    stream = torch.cuda.current_stream(model.device).cuda_stream
+    check(_lib.lib().b2_sample_min_p(model._h, lg.data_ptr(), B, V, float(p_base), u.data_ptr(), out.data_ptr(),
+                                     probs.data_ptr() if probs is not None else None, stream))
+    res = out[0:1] if one else out
+    return (res, probs) if return_probs else res
+
+
+def generate(prompt, tokenizer, model, max_tokens=20, streamer=None, kv_cache=None, config=None, generator=None):
+    """The reference's decode loop, quirks included (llama3.2_model_numpy.py:873-910): no EOS stop, BOS
+    only on the first call, and with a cache the text of the last sampled token is re-tokenised and fed
+    back."""
+    res = prompt
+    print(prompt, end="", flush=True)
+    for i in range(max_tokens):
+        if config.use_cache or kv_cache is not None:
+            input_ids = tokenizer(prompt, return_tensors="pt", add_special_tokens=(i == 0)).input_ids.numpy()
+        else:
+            input_ids = tokenizer(res, return_tensors="pt", add_special_tokens=True).input_ids.numpy()
+        input_ids = np.asarray(input_ids)
+        _, logits, kv_cache, _, _ = model(input_ids, use_cache=config.use_cache, kv_cache=kv_cache,
+                                          output_hidden_states=False, output_attentions=False,
+                                          logits_mode=LOGITS_LAST)
+        val = min_p_sampling(logits[-1], generator=generator, model=model)
+        prompt = tokenizer.decode(val.cpu())
+        res += prompt
+        print(prompt, end="", flush=True)
+    return res
+
+
+def load_sharded_safetensors_via_weight_map(model_dir, index_filename="model.safetensors.index.json"):
+    """Local-directory twin of llama3.2_model_numpy.py:981-1021 (index -> shards, single-file fallback,
+    config.json -> AttributeDict)."""
+    from safetensors.torch import load_file
+    all_tensors = {}
+    index_path = os.path.join(model_dir, index_filename)
+    if os.path.exists(index_path):
+        with open(index_path) as f:
+            weight_map = json.load(f).get("weight_map", {})
+        if not weight_map:
+            raise ValueError("The weight_map is missing or empty in the index file.")
+        for shard in sorted(set(weight_map.values())):
+            all_tensors.update(load_file(os.path.join(model_dir, shard)))
+    else:
+        all_tensors.update(load_file(os.path.join(model_dir, "model.safetensors")))
+    with open(os.path.join(model_dir, "config.json")) as f:
+        config = AttributeDict(json.load(f))
+    return all_tensors, config
+
+
+def load_model(model_name, device: int = 0):
+    """load_model (llama3.2_model_numpy.py:1030-1047).  ``model_name`` is a local snapshot directory
+    (there is no network here); a hub id is resolved through huggingface_hub when one is reachable."""
+    global weights
+    from transformers import AutoTokenizer
+    model_dir = model_name
+    if not os.path.isdir(model_dir):
+        from huggingface_hub import snapshot_download
+        model_dir = snapshot_download(repo_id=model_name)
+    tokenizer = AutoTokenizer.from_pretrained(model_dir, trust_remote_code=True)
+    weights, config = load_sharded_safetensors_via_weight_map(model_dir)
+    if "head_dim" not in config:
+        config["head_dim"] = config["hidden_size"] // config["num_attention_heads"]
+    is_gemma = "gemma" in str(config.get("model_type", "")).lower()
+    model = (Gemma2ForCausalLM if is_gemma else LlamaForCausalLM)(config, weights, device=device)
+    return tokenizer, model, config

@@ -1,0 +1,149 @@
+"""GPU parity of every hand-written kernel, called through the C ABI, against fp32 torch restatements
+of the reference's ops fed the same bf16-rounded inputs (SURVEY.md section 4 'per-kernel parity').
+Tolerances are stated per test."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import (DEV, bf16_randn, err_stats, interleave_gate_up, op_attention, op_gemm, op_qkv_rope,
+                      op_rmsnorm, ref_attention)
+
+
+@pytest.mark.parametrize("M,H", [(5, 256), (37, 2048), (300, 2304), (64, 3072)])
+def test_rmsnorm(M, H):
+    g = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, H, generator=g) * 3).to(DEV)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(DEV)
+    ob, of = op_rmsnorm(x, w, 1e-5, want_f32=True)
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w
+    assert (of - ref).abs().max() < 1e-5 * ref.abs().max() + 1e-6          # fp32 path: rounding only
+    assert (ob.float() - ref).abs().max() <= ref.abs().max() * 2 ** -8      # bf16 output rounding
+
+
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 256), (256, 512, 2048), (100, 256, 128), (1000, 768, 512),
+    (2048, 3072, 2048), (333, 2304, 2304),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("bn", [256, 128, 64])
+def test_gemm_f32(M, N, K, bn):
+    a, w = bf16_randn(M, K, seed=1), bf16_randn(N, K, seed=2)
+    out = op_gemm(a, w, epi=1, bn=bn)
+    ref = a.float() @ w.float().T
+    st = err_stats(out, ref)
+    # bf16 x bf16 products are exact in fp32; only accumulation order differs
+    assert st["max_abs"] <= 2e-3 * math.sqrt(K / 64) , st
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (77, 256, 128)])
+def test_gemm_bf16_and_softcap(M, N, K):
+    a, w = bf16_randn(M, K, seed=3), bf16_randn(N, K, seed=4)
+    ref = a.float() @ w.float().T
+    out = op_gemm(a, w, epi=0)
+    assert (out.float() - ref).abs().max() <= ref.abs().max() * 2 ** -8 + 1e-3
+    cap = 30.0
+    out = op_gemm(a, w, epi=1, softcap=cap)
+    assert (out - torch.tanh(ref / cap) * cap).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,bn,split", [(256, 256, 512, 256, 1), (64, 512, 1024, 64, 4), (64, 2048, 8192, 64, 4),
+                                            (16, 256, 2048, 32, 2), (2000, 2048, 2048, 256, 1)])
+def test_gemm_residual(M, N, K, bn, split):
+    a, w = bf16_randn(M, K, seed=5), bf16_randn(N, K, seed=6, std=0.05)
+    x0 = torch.randn(M, N, generator=torch.Generator().manual_seed(7)).to(DEV)
+    x = x0.clone()
+    op_gemm(a, w, epi=2, bn=bn, split_k=split, out=x)
+    ref = x0 + a.float() @ w.float().T
+    assert (x - ref).abs().max() < 2e-3 * math.sqrt(K / 64), err_stats(x, ref)
+
+
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("M,I,K,bn", [(256, 512, 256, 256), (90, 8192, 2048, 256), (64, 512, 256, 64)])
+def test_gemm_glu(M, I, K, bn, act):
+    a = bf16_randn(M, K, seed=8)
+    gate, up = bf16_randn(I, K, seed=9, std=0.05), bf16_randn(I, K, seed=10, std=0.05)
+    out = op_gemm(a, interleave_gate_up(gate, up), epi=4, bn=bn, act=act)
+    g, u = a.float() @ gate.float().T, a.float() @ up.float().T
+    actf = torch.nn.functional.silu(g) if act == 0 else torch.nn.functional.gelu(g, approximate="tanh")
+    ref = actf * u
+    assert (out.float() - ref).abs().max() <= ref.abs().max() * 2 ** -7 + 2e-3, err_stats(out.float(), ref)
+
+
+def _rope_ref(x, pos, HD, theta):
+    """rotate-half RoPE with the reference's fp32 table arithmetic (llama3.2_model_numpy.py:42-90)."""
+    inv = 1.0 / (theta ** (np.arange(0, HD, 2).astype(np.float32) / HD))
+    ang = (inv[None, :] * pos.astype(np.float32)[:, None]).astype(np.float32)
+    emb = np.concatenate([ang, ang], -1)
+    cos, sin = torch.from_numpy(np.cos(emb)).to(x.device), torch.from_numpy(np.sin(emb)).to(x.device)
+    h = HD // 2
+    rot = torch.cat([-x[..., h:], x[..., :h]], -1)
+    return x * cos[:, None, :] + rot * sin[:, None, :]
+
+
+@pytest.mark.parametrize("B,S,H,NH,NKV,HD,t0,bn", [(2, 12, 256, 4, 2, 64, 0, 256), (1, 200, 256, 2, 1, 128, 7, 256),
+                                                   (2, 9, 256, 2, 1, 256, 3, 256), (3, 1, 256, 4, 2, 64, 5, 64),
+                                                   (1, 300, 2048, 32, 8, 64, 0, 256)])
+def test_qkv_rope_and_cache_append(B, S, H, NH, NKV, HD, t0, bn):
+    theta, Tmax = 500000.0, t0 + S + 5
+    a = bf16_randn(B * S, H, seed=11)
+    w = bf16_randn((NH + 2 * NKV) * HD, H, seed=12, std=0.05)
+    q, kc, vc = op_qkv_rope(a, w, B, S, NH, NKV, HD, Tmax, t0, theta, bn=bn)
+    y = (a.float() @ w.float().T).view(B, S, NH + 2 * NKV, HD)
+    pos = np.arange(t0, t0 + S)
+    tol = lambda ref: ref.abs().max() * 2 ** -7 + 1e-3
+    for b in range(B):
+        qr = _rope_ref(y[b, :, :NH], pos, HD, theta)
+        kr = _rope_ref(y[b, :, NH:NH + NKV], pos, HD, theta)
+        vr = y[b, :, NH + NKV:]
+        assert (q.view(B, S, NH, HD)[b].float() - qr).abs().max() <= tol(qr)
+        assert (kc[b, :, t0:t0 + S].float().permute(1, 0, 2) - kr).abs().max() <= tol(kr)
+        assert (vc[b, :, t0:t0 + S].float().permute(1, 0, 2) - vr).abs().max() <= tol(vr)
+    assert kc[:, :, :t0].abs().max() == 0 and kc[:, :, t0 + S:].abs().max() == 0    # nothing outside the appended rows
+
+
+ATT_CASES = [
+    # B, S, NH, NKV, HD, t0, causal, window, softcap
+    (1, 128, 1, 1, 64, 0, 1, 0, 0.0),
+    (2, 12, 4, 2, 64, 0, 1, 0, 0.0),
+    (1, 2, 4, 2, 64, 0, 0, 0, 0.0),        # the reference's q_len <= 2 quirk: unmasked
+    (1, 300, 4, 2, 64, 0, 1, 0, 0.0),
+    (2, 520, 8, 2, 64, 0, 1, 0, 0.0),
+    (1, 260, 2, 1, 128, 0, 1, 0, 0.0),
+    (1, 200, 2, 1, 256, 0, 1, 0, 0.0),
+    (1, 130, 4, 2, 64, 70, 1, 0, 0.0),     # chunk on a non-empty cache (always_causal extension)
+    (1, 400, 2, 1, 64, 0, 1, 100, 0.0),    # sliding window
+    (1, 300, 2, 1, 256, 0, 1, 64, 50.0),   # Gemma-2 HF flags: window + soft-cap
+    (1, 2048, 2, 1, 64, 0, 1, 0, 0.0),
+]
+
+
+@pytest.mark.parametrize("B,S,NH,NKV,HD,t0,causal,window,softcap", ATT_CASES)
+def test_attention_prefill(B, S, NH, NKV, HD, t0, causal, window, softcap):
+    Tmax = t0 + S + 3
+    q = bf16_randn(B * S, NH * HD, seed=13)
+    kc, vc = bf16_randn(B, NKV, Tmax, HD, seed=14), bf16_randn(B, NKV, Tmax, HD, seed=15)
+    scale = 1.0 / math.sqrt(HD)
+    out = op_attention(q, kc, vc, B, S, NH, NKV, HD, Tmax, t0, scale, softcap, causal, window)
+    ref = ref_attention(q, kc, vc, B, S, NH, NKV, HD, t0, scale, softcap, causal, window)
+    st = err_stats(out.float(), ref)
+    # P is rounded to bf16 before P.V and the output is bf16: ~2^-8 relative on O(1) values
+    assert st["max_abs"] <= 2e-2, st
+
+
+@pytest.mark.parametrize("B,NH,NKV,HD,t0,window,softcap", [(3, 4, 2, 64, 0, 0, 0.0), (2, 32, 8, 64, 143, 0, 0.0),
+                                                          (2, 24, 8, 128, 77, 0, 0.0), (2, 8, 4, 256, 300, 64, 50.0),
+                                                          (64, 32, 8, 64, 2100, 0, 0.0)])
+def test_attention_decode(B, NH, NKV, HD, t0, window, softcap):
+    Tmax = t0 + 4
+    q = bf16_randn(B, NH * HD, seed=16)
+    kc, vc = bf16_randn(B, NKV, Tmax, HD, seed=17), bf16_randn(B, NKV, Tmax, HD, seed=18)
+    scale = 1.0 / math.sqrt(HD)
+    out = op_attention(q, kc, vc, B, 1, NH, NKV, HD, Tmax, t0, scale, softcap, 0, window, decode=1)
+    ref = ref_attention(q, kc, vc, B, 1, NH, NKV, HD, t0, scale, softcap, 1, window)
+    assert (out.float() - ref).abs().max() <= 1e-2, err_stats(out.float(), ref)

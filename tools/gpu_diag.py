@@ -1,0 +1,95 @@
+"""Bring-up diagnostics (run on the GPU box): each stage in its own process so a trap cannot hide the rest.
+usage: python tools/gpu_diag.py <stage>     stages: info gemm attn attn_variants"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+
+
+def stage_info():
+    print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0), torch.version.cuda)
+    p = torch.cuda.get_device_properties(0)
+    print("SMs", p.multi_processor_count, "mem GB", p.total_memory / 2**30)
+    from llm_np_cp_b200 import _lib
+    print("b2_device_count", _lib.lib().b2_device_count())
+
+
+def stage_gemm():
+    from gpu_util import bf16_randn, op_gemm
+    for (M, N, K, bn) in [(128, 256, 64, 256), (128, 256, 128, 256), (128, 64, 64, 64), (256, 512, 256, 256), (4096, 4096, 4096, 256)]:
+        a, w = bf16_randn(M, K, seed=1), bf16_randn(N, K, seed=2)
+        out = op_gemm(a, w, epi=1, bn=bn)
+        ref = a.float() @ w.float().T
+        d = (out - ref).abs()
+        print(f"gemm M{M} N{N} K{K} bn{bn}: max_abs {d.max().item():.4g} ref_absmax {ref.abs().max().item():.4g} "
+              f"out_absmax {out.abs().max().item():.4g} frac_bad {(d > 1e-2).float().mean().item():.4f}")
+        if d.max() > 1e-2:
+            bad = (d > 1e-2)
+            print("  bad rows (first 16):", torch.nonzero(bad.any(1)).flatten()[:16].tolist())
+            print("  bad cols (first 16):", torch.nonzero(bad.any(0)).flatten()[:16].tolist())
+            print("  out[0,:8]", out[0, :8].tolist(), "ref[0,:8]", ref[0, :8].tolist())
+            # is it a K-slice problem?  compare against partial-K references
+            for kk in range(16, K + 1, 16):
+                r2 = a[:, :kk].float() @ w[:, :kk].float().T
+                if (out - r2).abs().max() < 1e-2:
+                    print(f"  matches partial K={kk}")
+    # timing of a big one
+    M = N = K = 8192
+    a, w = bf16_randn(M, K, seed=1), bf16_randn(N, K, seed=2)
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    for _ in range(2):
+        op_gemm(a, w, epi=0, out=out)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(5):
+        op_gemm(a, w, epi=0, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"gemm 8192^3 bf16: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    ref = a[:256].float() @ w.float().T
+    print("  8192 check max_abs", (out[:256].float() - ref).abs().max().item(), "ref absmax", ref.abs().max().item())
+
+
+def attn_case(B, S, NH, NKV, HD, t0=0, causal=1, window=0, softcap=0.0):
+    from gpu_util import bf16_randn, op_attention, ref_attention
+    Tmax = t0 + S + 3
+    q = bf16_randn(B * S, NH * HD, seed=13)
+    kc, vc = bf16_randn(B, NKV, Tmax, HD, seed=14), bf16_randn(B, NKV, Tmax, HD, seed=15)
+    scale = 1.0 / math.sqrt(HD)
+    out = op_attention(q, kc, vc, B, S, NH, NKV, HD, Tmax, t0, scale, softcap, causal, window)
+    ref = ref_attention(q, kc, vc, B, S, NH, NKV, HD, t0, scale, softcap, causal, window)
+    d = (out.float() - ref).abs()
+    return d.max().item(), d.mean().item(), out, ref
+
+
+def stage_attn():
+    for case in [(1, 128, 1, 1, 64), (1, 16, 1, 1, 64), (1, 300, 2, 1, 64), (1, 128, 1, 1, 128), (1, 128, 1, 1, 256), (2, 2048, 8, 2, 64)]:
+        mx, mean, out, ref = attn_case(*case)
+        print(f"attn {case}: max_abs {mx:.4g} mean_abs {mean:.4g} out_absmax {out.float().abs().max().item():.4g} ref_absmax {ref.abs().max().item():.4g}")
+        if mx > 5e-2:
+            print("   out[0,:8]", out[0, :8].float().tolist())
+            print("   ref[0,:8]", ref[0, :8].tolist())
+            print("   out[5,:8]", out[5, :8].float().tolist())
+            print("   ref[5,:8]", ref[5, :8].tolist())
+
+
+def stage_attn_variants():
+    for HD, bnkv in [(64, 128), (128, 128)]:
+        for lbo, sbo in [(0, 0), (1024, bnkv * 128), (128, 1024), (1024, 128), (bnkv * 128, 128), (16, 1024), (2048, 1024)]:
+            os.environ["B2_V_LBO"], os.environ["B2_V_SBO"] = str(lbo), str(sbo)
+            try:
+                mx, mean, _, _ = attn_case(1, 128, 1, 1, HD)
+                print(f"HD{HD} v_lbo={lbo} v_sbo={sbo}: max_abs {mx:.4g} mean_abs {mean:.4g}")
+            except Exception as e:
+                print(f"HD{HD} v_lbo={lbo} v_sbo={sbo}: EXC {e}")
+                return
+
+
+if __name__ == "__main__":
+    globals()["stage_" + sys.argv[1]]()
