@@ -91,7 +91,7 @@ int b2_cache_read(const b2_cache* c, int layer, int which /*0=K,1=V*/, int batch
  *             B2_ERR_ARG like the reference raises (App. B Q4) unless cfg.always_causal is set.
  * logits_dev  fp32 output per logits_mode (may be NULL with B2_LOGITS_NONE)
  * hidden_dev  optional fp32 [L+1,B,S,H]: the reference's hidden_states tuple (:693-720) for parity tests
- * stream      cudaStream_t (NULL = the engine's own stream)                                   */
+ * stream      cudaStream_t; NULL is the CUDA default stream, as everywhere in CUDA              */
 int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids_dev, int B, int S, int logits_mode,
                float* logits_dev, float* hidden_dev, void* stream);
 /* Same call with HOST buffers (pageable or pinned): ids H2D, forward, logits D2H, synchronises. */

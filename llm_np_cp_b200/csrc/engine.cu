@@ -577,6 +577,8 @@ extern "C" int b2_finalize(b2_engine* e) {
   for (size_t i = 0; i < e->layers.size(); ++i)
     if ((e->layers[i].loaded & need) != need)
       return fail(B2_ERR_STATE, "layer %zu is missing tensors (have mask 0x%x, need 0x%x)", i, e->layers[i].loaded, need);
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());       // pageable H2D copies may still be in flight on the default stream
   e->finalized = true;
   return B2_OK;
 }
@@ -600,6 +602,7 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
   CK(cudaMalloc(&c->t0_dev, 4));
   CK(cudaMemset(c->t0_dev, 0, 4));
+  CK(cudaDeviceSynchronize());       // cudaMemset is asynchronous; callers may use non-blocking streams
   *out = c;
   return B2_OK;
 }
@@ -608,8 +611,10 @@ extern "C" int b2_cache_reset(b2_cache* c) {
   if (!c) return fail(B2_ERR_ARG, "null cache");
   CK(cudaSetDevice(c->e->device));
   CK(cudaStreamSynchronize(c->e->stream));
+  CK(cudaDeviceSynchronize());
   c->len = 0;
   CK(cudaMemset(c->t0_dev, 0, 4));
+  CK(cudaDeviceSynchronize());
   return B2_OK;
 }
 static bf16* cache_k(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2) * c->plane; }
@@ -624,8 +629,8 @@ extern "C" int b2_cache_read(const b2_cache* c, int layer, int which, int batch,
   // [batch*NKV] slabs of [len, HD] out of [max_tokens, HD]
   CK(cudaMemcpy2DAsync(dev_out, static_cast<size_t>(c->len) * g.head_dim * 2, src,
                        static_cast<size_t>(c->max_tokens) * g.head_dim * 2, static_cast<size_t>(c->len) * g.head_dim * 2,
-                       static_cast<size_t>(batch) * g.num_key_value_heads, cudaMemcpyDeviceToDevice, c->e->stream));
-  CK(cudaStreamSynchronize(c->e->stream));
+                       static_cast<size_t>(batch) * g.num_key_value_heads, cudaMemcpyDeviceToDevice, 0));
+  CK(cudaDeviceSynchronize());
   return B2_OK;
 }
 
@@ -815,7 +820,7 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
   if (B <= 0 || S <= 0) return fail(B2_ERR_ARG, "B and S must be positive");
   if (logits_mode != B2_LOGITS_NONE && !logits) return fail(B2_ERR_ARG, "logits buffer is null");
   CK(cudaSetDevice(e->device));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the CUDA (legacy) default stream
   const b2_config& c = e->cfg;
   b2_cache* kc = cache;
   if (!kc) {  // use_cache=False: attention over this call's tokens only
@@ -916,7 +921,7 @@ extern "C" int b2_sample_min_p(b2_engine* e, const float* logits, int B, int ld,
                                int64_t* out_ids, float* probs, void* stream) {
   if (!e || !logits || !u || !out_ids || B <= 0) return fail(B2_ERR_ARG, "bad sample arguments");
   CK(cudaSetDevice(e->device));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the CUDA (legacy) default stream
   min_p_sample_kernel<<<B, 1024, 0, st>>>(logits, ld, e->cfg.vocab_size, p_base, u, reinterpret_cast<long long*>(out_ids), probs);
   CK(cudaGetLastError());
   e->st.launches++;

@@ -91,5 +91,89 @@ def stage_attn_variants():
                 return
 
 
+
+
+def stage_model():
+    from oracle import np_oracle as O
+    import llm_np_cp_b200 as M
+    cfg = O.llama_config("tiny")
+    w = O.synth_weights(cfg, 1, 0.08, 0.1)
+    Wn = O.to_numpy_f32(w)
+    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w)
+    for (B, S) in [(2, 12), (1, 12), (1, 2), (1, 9), (2, 5), (1, 16), (1, 200), (2, 12)]:
+        ids = np.random.default_rng(B * 100 + S).integers(0, cfg.vocab_size, (B, S))
+        want = O.forward(cfg, Wn, ids)
+        _, lg, _, hs, _ = model(ids, use_cache=False)
+        errs = [float(np.abs(h.cpu().numpy() - wh).max()) for h, wh in zip(hs, want.hidden_states)]
+        d = np.abs(lg.cpu().numpy() - want.logits)
+        rows = d.reshape(B * S, -1).max(1)
+        print(f"B{B} S{S}: logits max {d.max():.4g}; hidden max errs {['%.3g' % e for e in errs]}; bad rows {np.nonzero(rows > 0.3)[0][:20].tolist()}")
+        h1 = hs[1].cpu().numpy().reshape(B * S, -1)
+        w1 = want.hidden_states[1].reshape(B * S, -1)
+        print("    layer-1 row errs:", ["%.2g" % e for e in np.abs(h1 - w1).max(1)[:24]])
+
+
+def stage_fresh():
+    from oracle import np_oracle as O
+    import llm_np_cp_b200 as M
+    cfg = O.llama_config("tiny")
+    w = O.synth_weights(cfg, 1, 0.08, 0.1)
+    Wn = O.to_numpy_f32(w)
+    keep = []
+    for (B, S) in [(1, 2), (1, 9), (2, 12), (1, 200), (2, 5), (1, 12), (2, 2)]:
+        model = M.LlamaForCausalLM(M.AttributeDict(cfg), w)
+        keep.append(model)
+        ids = np.random.default_rng(0).integers(0, cfg.vocab_size, (B, S))
+        want = O.forward(cfg, Wn, ids)
+        for rep in range(2):
+            _, lg, _, hs, _ = model(ids, use_cache=False)
+            errs = [float(np.abs(h.cpu().numpy() - wh).max()) for h, wh in zip(hs, want.hidden_states)]
+            d = np.abs(lg.cpu().numpy() - want.logits)
+            h1 = hs[1].cpu().numpy().reshape(B * S, -1)
+            w1 = want.hidden_states[1].reshape(B * S, -1)
+            print(f"fresh B{B} S{S} rep{rep}: logits max {d.max():.4g}; hidden errs {['%.3g' % e for e in errs]}; "
+                  f"layer1 row errs {['%.2g' % e for e in np.abs(h1 - w1).max(1)[:12]]}")
+
+
+def stage_destroy():
+    import gc
+    from oracle import np_oracle as O
+    import llm_np_cp_b200 as M
+    from conftest import load_golden
+    cfg = O.llama_config("tiny")
+    w = O.synth_weights(cfg, 1, 0.08, 0.1)
+    Wn = O.to_numpy_f32(w)
+
+    def run(B, S, tag):
+        model = M.LlamaForCausalLM(M.AttributeDict(cfg), w)
+        ids = np.random.default_rng(0).integers(0, cfg.vocab_size, (B, S))
+        want = O.forward(cfg, Wn, ids)
+        _, lg, _, hs, _ = model(ids, use_cache=False)
+        errs = [float(np.abs(h.cpu().numpy() - wh).max()) for h, wh in zip(hs, want.hidden_states)]
+        d = np.abs(lg.cpu().numpy() - want.logits)
+        print(f"{tag} B{B} S{S}: logits max {d.max():.4g}; hidden errs {['%.3g' % e for e in errs]}", flush=True)
+        return model
+
+    m = run(2, 12, "first")
+    del m
+    gc.collect()
+    print("destroyed engine 1", flush=True)
+    m2 = run(1, 2, "after-destroy")
+    m3 = run(1, 9, "after-destroy(no destroy between)")
+    del m2, m3
+    gc.collect()
+    m4 = run(2, 12, "after-destroy-2")
+    m5 = run(1, 2, "no-destroy")
+    # golden flow
+    for name in ["llama_tiny_prefill", "llama_tiny_qlen2"]:
+        meta, arr = load_golden(name)
+        model = M.LlamaForCausalLM(M.AttributeDict(cfg), O.synth_weights(cfg, meta["wseed"], meta["std"], meta["jitter"]))
+        _, lg, _, hs, _ = model(arr["ids"], use_cache=False)
+        d = np.abs(lg.cpu().numpy() - arr["logits"])
+        print(f"golden {name}: logits max {d.max():.4g}", flush=True)
+        del model
+        gc.collect()
+
+
 if __name__ == "__main__":
     globals()["stage_" + sys.argv[1]]()
