@@ -743,8 +743,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     if (!c.gemma) {
       GemmParams p = base_params(M, H, e->q_cols);
       p.out = e->x; p.ldo = H;
-      if (M <= 128) p.split_k = (e->q_cols / 64) % 4 == 0 ? 4 : 1;
-      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_RESID, e->att, e->q_cols, Ly.wo, p));   // x += attn . Wo^T
+      CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->att, e->q_cols, Ly.wo, p));   // x += attn . Wo^T
       CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M));
     } else {
       GemmParams p = base_params(M, H, e->q_cols);
@@ -763,8 +762,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     if (!c.gemma) {
       GemmParams p = base_params(M, H, I);
       p.out = e->x; p.ldo = H;
-      if (M <= 128) p.split_k = (I / 64) % 4 == 0 ? 4 : 1;
-      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_RESID, e->hb, I, Ly.wd, p));              // x += h . Wd^T
+      CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->hb, I, Ly.wd, p));              // x += h . Wd^T
     } else {
       GemmParams p = base_params(M, H, I);
       p.out = e->y; p.ldo = H;
@@ -855,11 +853,13 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
       add_scalar_kernel<<<1, 32, 0, st>>>(kc->t0_dev, -S);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));
+      // the legacy default stream cannot be captured: record on the engine's own stream, replay on `st`
+      cudaStream_t cs = e->stream;
       cudaGraph_t g;
       e->capturing = true;
-      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int r = run_layers(e, kc, st, ids, B, S, logits_mode, logits, nullptr);
-      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      int r = run_layers(e, kc, cs, ids, B, S, logits_mode, logits, nullptr);
+      cudaError_t ce = cudaStreamEndCapture(cs, &g);
       e->capturing = false;
       CKR(r);
       CK(ce);
