@@ -83,6 +83,8 @@ int b2_cache_read(const b2_cache* c, int layer, int which /*0=K,1=V*/, int batch
 #define B2_LOGITS_NONE 0
 #define B2_LOGITS_ALL 1    /* [B,S,V] fp32 -- what the reference returns (:811) */
 #define B2_LOGITS_LAST 2   /* [B,V] fp32, last position only -- what generate() consumes (:899) */
+#define B2_LOGITS_ALL_LAST_TO_HOST 3 /* b2_forward_host only: [B,S,V] computed and kept on the device (as the
+                                        reference's CuPy twin does), the last position [B,V] copied to the host */
 
 /* -------- forward: LlamaForCausalLM_np.__call__ / Gemma2ForCausalLM_np.__call__
  * ids_dev     int64 [B,S] on the device

@@ -880,15 +880,18 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
 extern "C" int b2_forward_host(b2_engine* e, b2_cache* cache, const int64_t* ids_host, int B, int S, int logits_mode,
                                float* logits_host, float* hidden_host) {
   if (!e || !ids_host) return fail(B2_ERR_ARG, "null argument");
+  if (B <= 0 || S <= 0) return fail(B2_ERR_ARG, "B and S must be positive");
   CK(cudaSetDevice(e->device));
   CKR(ensure_ws(e, B * S, B));
   const b2_config& c = e->cfg;
-  const size_t M = static_cast<size_t>(B) * S;
-  size_t need = logits_mode == B2_LOGITS_ALL ? M * c.vocab_size : (logits_mode == B2_LOGITS_LAST ? static_cast<size_t>(B) * c.vocab_size : 0);
+  const size_t M = static_cast<size_t>(B) * S, V = c.vocab_size;
+  const bool all_dev = logits_mode == B2_LOGITS_ALL || logits_mode == B2_LOGITS_ALL_LAST_TO_HOST;
+  const size_t need = all_dev ? M * V : (logits_mode == B2_LOGITS_LAST ? static_cast<size_t>(B) * V : 0);
   if (need > e->logits_ws_elems) {
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaDeviceSynchronize());
     cudaFree(e->logits_ws);
     e->logits_ws = nullptr;
+    e->logits_ws_elems = 0;
     CK(cudaMalloc(&e->logits_ws, need * 4));
     e->logits_ws_elems = need;
   }
@@ -896,9 +899,14 @@ extern "C" int b2_forward_host(b2_engine* e, b2_cache* cache, const int64_t* ids
   const size_t hid_elems = static_cast<size_t>(c.num_hidden_layers + 1) * M * c.hidden_size;
   if (hidden_host) CK(cudaMalloc(&hidden_dev, hid_elems * 4));
   CK(cudaMemcpyAsync(e->ids_ws, ids_host, M * 8, cudaMemcpyHostToDevice, e->stream));
-  int r = b2_forward(e, cache, e->ids_ws, B, S, logits_mode, e->logits_ws, hidden_dev, e->stream);
-  if (r == B2_OK && need) {
-    cudaError_t ce = cudaMemcpyAsync(logits_host, e->logits_ws, need * 4, cudaMemcpyDeviceToHost, e->stream);
+  int r = b2_forward(e, cache, e->ids_ws, B, S, all_dev ? B2_LOGITS_ALL : logits_mode, e->logits_ws, hidden_dev, e->stream);
+  if (r == B2_OK && need && logits_host) {
+    cudaError_t ce;
+    if (logits_mode == B2_LOGITS_ALL_LAST_TO_HOST)   // all positions computed on the device, last rows read back
+      ce = cudaMemcpy2DAsync(logits_host, V * 4, e->logits_ws + (static_cast<size_t>(S) - 1) * V, static_cast<size_t>(S) * V * 4,
+                             V * 4, B, cudaMemcpyDeviceToHost, e->stream);
+    else
+      ce = cudaMemcpyAsync(logits_host, e->logits_ws, need * 4, cudaMemcpyDeviceToHost, e->stream);
     if (ce != cudaSuccess) r = fail(B2_ERR_CUDA, "logits D2H failed: %s", cudaGetErrorString(ce));
   }
   if (r == B2_OK && hidden_host) {

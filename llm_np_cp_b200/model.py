@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from ._lib import B2Config, B2Stats, check
 
-LOGITS_NONE, LOGITS_ALL, LOGITS_LAST = 0, 1, 2
+LOGITS_NONE, LOGITS_ALL, LOGITS_LAST, LOGITS_ALL_LAST_TO_HOST = 0, 1, 2, 3
 
 
 class AttributeDict(dict):
