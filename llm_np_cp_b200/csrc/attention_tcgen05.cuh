@@ -46,6 +46,80 @@ struct AttnCfg {
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
 };
 
+
+// ---- per-row softmax pieces (thread = q row).  Mask test: column cc is valid iff (unsigned)(cc - lo) < span.
+template <int SCH, bool MASK>
+__device__ __forceinline__ float att_row_max(uint32_t tS_row, int lo, unsigned span) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < SCH; ++c) {
+    uint32_t sr[32];
+    tmem_ld32(tS_row + c * 32, sr);
+    tmem_ld_wait();
+    const int rel = c * 32 - lo;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float v0 = __uint_as_float(sr[i]), v1 = __uint_as_float(sr[i + 1]);
+      float v2 = __uint_as_float(sr[i + 2]), v3 = __uint_as_float(sr[i + 3]);
+      if (MASK) {
+        v0 = static_cast<unsigned>(rel + i) < span ? v0 : -INFINITY;
+        v1 = static_cast<unsigned>(rel + i + 1) < span ? v1 : -INFINITY;
+        v2 = static_cast<unsigned>(rel + i + 2) < span ? v2 : -INFINITY;
+        v3 = static_cast<unsigned>(rel + i + 3) < span ? v3 : -INFINITY;
+      }
+      m0 = fmaxf(m0, v0);
+      m1 = fmaxf(m1, v1);
+      m2 = fmaxf(m2, v2);
+      m3 = fmaxf(m3, v3);
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// P = exp2(x - m) with x = s*sl2 (or the soft-capped score in log2 units); bf16 P -> 128B-swizzled smem rows
+// (the K-major A operand of P.V); returns the row sum of the fp32 probabilities.
+template <int SCH, bool MASK, bool CAP>
+__device__ __forceinline__ float att_row_exp(uint32_t tS_row, uint8_t* sP, int r, float sl2, float m_safe, float cap_in,
+                                             float cap_out, int lo, unsigned span) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < SCH; ++c) {
+    uint32_t sr[32];
+    tmem_ld32(tS_row + c * 32, sr);
+    tmem_ld_wait();
+    const int rel = c * 32 - lo;
+    float e[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float sv = __uint_as_float(sr[i]);
+      float x;
+      if (CAP) x = fmaf(fast_tanh(sv * cap_in), cap_out, -m_safe);   // cap*log2e*tanh(s*scale/cap) - m
+      else x = fmaf(sv, sl2, -m_safe);
+      if (MASK) x = static_cast<unsigned>(rel + i) < span ? x : -INFINITY;
+      e[i] = fast_exp2(x);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      s0 += e[i];
+      s1 += e[i + 1];
+      s2 += e[i + 2];
+      s3 += e[i + 3];
+    }
+    uint8_t* prow = sP + (c >> 1) * (ATT_BM * 128) + r * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16(e[8 * i + 0], e[8 * i + 1]);
+      u.y = pack_bf16(e[8 * i + 2], e[8 * i + 3]);
+      u.z = pack_bf16(e[8 * i + 4], e[8 * i + 5]);
+      u.w = pack_bf16(e[8 * i + 6], e[8 * i + 7]);
+      const int chunk16 = (c & 1) * 4 + i;
+      *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
+    }
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, (HD == 64) ? 2 : 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -195,6 +269,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int qpos = t0 + q0 + r;                   // absolute position of this query
     const float LOG2E = 1.4426950408889634f;
     const float sl2 = p.scale * LOG2E;
+    const bool cap = p.softcap > 0.f;
+    const float cap_in = cap ? p.scale / p.softcap : 0.f, cap_out = p.softcap * LOG2E;
     float m_used = -INFINITY;                        // running max (log2 domain) the P values are scaled by
     float l = 0.f;                                   // running denominator
     for (int it = 0; it < n_tiles; ++it) {
@@ -209,29 +285,15 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         hi = min(BNKV, last - kv0 + 1);
         if (p.window > 0) lo = max(0, qpos - p.window + 1 - kv0);
       }
+      const unsigned span = hi > lo ? static_cast<unsigned>(hi - lo) : 0u;
       mbar_wait(bar_s, it & 1);
       tc_fence_after();
       // ---- pass 1: row max of the raw scores ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < SCH; ++c) {
-        uint32_t sr[32];
-        tmem_ld32(tS + lane_off + c * 32, sr);
-        tmem_ld_wait();
-        if (need_mask) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int cc = c * 32 + i;
-            if (cc >= lo && cc < hi) mx = fmaxf(mx, __uint_as_float(sr[i]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
-        }
-      }
+      const float mx = need_mask ? att_row_max<SCH, true>(tS + lane_off, lo, span)
+                                 : att_row_max<SCH, false>(tS + lane_off, lo, span);
       float m_tile = mx;                            // -> log2 domain, after the optional soft-cap
       if (mx != -INFINITY) {
-        if (p.softcap > 0.f) m_tile = p.softcap * tanhf(mx * p.scale / p.softcap) * LOG2E;
+        if (cap) m_tile = cap_out * fast_tanh(mx * cap_in);
         else m_tile = mx * sl2;
       }
       // ---- lazy rescale of O / l ----
@@ -259,39 +321,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       // ---- pass 2: P = exp2(s - m), row sum, bf16 P -> swizzled smem (K-major SW128 A operand) ----
       const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < SCH; ++c) {
-        uint32_t sr[32];
-        tmem_ld32(tS + lane_off + c * 32, sr);
-        tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(sr[i]);
-          float e;
-          if (p.softcap > 0.f) e = fast_exp2(p.softcap * tanhf(s * p.scale / p.softcap) * LOG2E - m_safe);
-          else e = fast_exp2(fmaf(s, sl2, -m_safe));
-          if (need_mask) {
-            const int cc = c * 32 + i;
-            if (cc < lo || cc >= hi) e = 0.f;
-          }
-          // the MMA sees bf16 P; accumulate the denominator from the same rounded values
-          e = __bfloat162float(__float2bfloat16_rn(e));
-          lsum += e;
-          pv[i] = e;
-        }
-        uint8_t* prow = sP + (c >> 1) * (ATT_BM * 128) + r * 128;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16(pv[8 * i + 0], pv[8 * i + 1]);
-          u.y = pack_bf16(pv[8 * i + 2], pv[8 * i + 3]);
-          u.z = pack_bf16(pv[8 * i + 4], pv[8 * i + 5]);
-          u.w = pack_bf16(pv[8 * i + 6], pv[8 * i + 7]);
-          const int chunk16 = (c & 1) * 4 + i;
-          *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
-        }
+      float lsum;
+      if (cap) {
+        lsum = need_mask ? att_row_exp<SCH, true, true>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
+                         : att_row_exp<SCH, false, true>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
+      } else {
+        lsum = need_mask ? att_row_exp<SCH, true, false>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
+                         : att_row_exp<SCH, false, false>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
       }
       l += lsum;
       fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the MMA

@@ -175,5 +175,32 @@ def stage_destroy():
         gc.collect()
 
 
+def stage_attn_perf():
+    import ctypes
+    from gpu_util import bf16_randn, L, stream
+    from llm_np_cp_b200 import _lib
+    for (B, S, NH, NKV, HD) in [(8, 2048, 32, 8, 64), (2, 2048, 32, 8, 64), (1, 8192, 24, 8, 128), (2, 4096, 8, 4, 256)]:
+        Tmax = S
+        q = bf16_randn(B * S, NH * HD, seed=13)
+        kc, vc = bf16_randn(B, NKV, Tmax, HD, seed=14), bf16_randn(B, NKV, Tmax, HD, seed=15)
+        out = torch.zeros((B * S, NH * HD), dtype=torch.bfloat16, device="cuda")
+        scale = 1.0 / math.sqrt(HD)
+        def run():
+            _lib.check(L().b2_op_attention(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), out.data_ptr(), B, S, NH, NKV, HD,
+                                           Tmax, 0, float(scale), 0.0, 1, 0, 0, stream()))
+        run(); run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        n = 5
+        for _ in range(n):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        fl = 4.0 * B * NH * HD * S * (S + 1) / 2
+        print(f"attn B{B} S{S} NH{NH} NKV{NKV} HD{HD}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (causal flops)", flush=True)
+
+
 if __name__ == "__main__":
     globals()["stage_" + sys.argv[1]]()
