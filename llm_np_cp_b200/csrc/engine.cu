@@ -89,23 +89,28 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-// 2-D bf16 row-major tensor [rows, cols] (cols contiguous), box = {64 columns (128 B), box_rows}, 128B swizzle
-static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                     uint32_t box_rows) {
+// 2-D row-major tensor [rows, cols] (cols contiguous), 128-byte-wide box rows, 128B swizzle.
+// bf16: box = {64 columns, box_rows} (MMA operand tiles); fp32: box = {32 columns, box_rows} (epilogue slabs).
+static int make_tmap_t(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                       uint32_t box_rows, bool f32) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const uint64_t esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld_elems * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u ptr=%p",
+    return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u ptr=%p f32=%d",
                 static_cast<int>(r), (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems,
-                box_rows, ptr);
+                box_rows, ptr, (int)f32);
   return B2_OK;
+}
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+  return make_tmap_t(m, ptr, rows, cols, ld_elems, box_rows, false);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -135,7 +140,8 @@ static int num_sms() {
 }
 
 template <int BN, int EPI>
-static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                         cudaStream_t st) {
   auto kern = gemm_bf16_kernel<BN, EPI>;
   static bool attr[16] = {false};
   int dev = 0;
@@ -147,21 +153,23 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM, n_blocks = (p.N + BN - 1) / BN;
   const int total = m_blocks * n_blocks * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, tc, p);
   CK(cudaGetLastError());
   return B2_OK;
 }
 
-static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       cudaStream_t st) {
+// tc: fp32 output map ({32 x 32} boxes) for EPI_F32 / EPI_RESID; any valid map otherwise (unused)
+static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                       const GemmParams& p, cudaStream_t st) {
   if (p.K % GEMM_BK != 0 || p.K <= 0) return fail(B2_ERR_ARG, "GEMM K=%d must be a positive multiple of 64", p.K);
   if (p.N % 32 != 0) return fail(B2_ERR_ARG, "GEMM N=%d must be a multiple of 32", p.N);
   if (epi == EPI_GLU && p.N % 64 != 0) return fail(B2_ERR_ARG, "GLU GEMM N=%d must be a multiple of 64", p.N);
   if (p.split_k < 1 || (p.K / GEMM_BK) % p.split_k != 0)
     return fail(B2_ERR_ARG, "split_k=%d must divide K/64=%d", p.split_k, p.K / GEMM_BK);
   if (p.split_k > 1 && epi != EPI_RESID) return fail(B2_ERR_ARG, "split_k needs the residual epilogue");
+  if ((epi == EPI_F32 || epi == EPI_RESID) && p.ldo % 4 != 0) return fail(B2_ERR_ARG, "fp32 output stride %d must be a multiple of 4", p.ldo);
 #define GEMM_CASE(BN_, EPI_) \
-  if (bn == BN_ && epi == EPI_) return launch_gemm_t<BN_, EPI_>(ta, tb, p, st)
+  if (bn == BN_ && epi == EPI_) return launch_gemm_t<BN_, EPI_>(ta, tb, tc, p, st)
   GEMM_CASE(256, EPI_BF16);
   GEMM_CASE(256, EPI_F32);
   GEMM_CASE(256, EPI_RESID);
@@ -321,7 +329,7 @@ struct b2_engine {
   float* logits_ws = nullptr;
   size_t logits_ws_elems = 0;
   b2_cache* scratch = nullptr;  // used when the caller passes no cache (use_cache=False)
-  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, bool>, CUtensorMap> tmaps;
   Stats st;
   bool decode_graph = false;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -329,12 +337,13 @@ struct b2_engine {
 };
 
 static int get_tmap(b2_engine* e, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                    const CUtensorMap** out) {
-  auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+                    const CUtensorMap** out, bool f32 = false) {
+  auto key = std::make_tuple(ptr, rows, cols, ld, box_rows, f32);
   auto it = e->tmaps.find(key);
   if (it == e->tmaps.end()) {
+    if (e->tmaps.size() > 4096) e->tmaps.clear();   // caller-provided output pointers may keep changing
     CUtensorMap m;
-    CKR(make_tmap(&m, ptr, rows, cols, ld, box_rows));
+    CKR(make_tmap_t(&m, ptr, rows, cols, ld, box_rows, f32));
     it = e->tmaps.emplace(key, m).first;
   }
   *out = &it->second;
@@ -362,13 +371,25 @@ static void time_end(b2_engine* e, cudaStream_t st) {
   cudaEventRecord(e->st.used.back().b, st);
 }
 
+// rasterisation band: if W fits comfortably in L2 keep bands short (A streams from HBM once); otherwise
+// make them long enough to amortise re-reading W once per band
+static int pick_band(int N, int K) {
+  const double w_bytes = 2.0 * N * K;
+  return w_bytes <= 48e6 ? 8 : 32;
+}
+
 // C = A . W^T through the engine (cached descriptors, stats)
-static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* a, int lda, const bf16* w, GemmParams p) {
-  const CUtensorMap *ta, *tb;
-  CKR(get_tmap(e, a, e->ws_tokens > p.M ? e->ws_tokens : p.M, p.K, lda, GEMM_BM, &ta));
+static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* a, int lda, const bf16* w, GemmParams p,
+                    int a_rows = 0) {
+  const CUtensorMap *ta, *tb, *tc;
+  if (!a_rows) a_rows = e->ws_tokens > p.M ? e->ws_tokens : p.M;
+  CKR(get_tmap(e, a, a_rows, p.K, lda, GEMM_BM, &ta));
   CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, bn, &tb));
+  tc = ta;
+  if (epi == EPI_F32 || epi == EPI_RESID) CKR(get_tmap(e, p.out, p.M, p.N, p.ldo, 32, &tc, true));
+  p.band_m = pick_band(p.N, p.k_wrap);
   time_begin(e, st, 2.0 * p.M * static_cast<double>(p.N) * p.K, 0);
-  int r = launch_gemm(bn, epi, *ta, *tb, p, st);
+  int r = launch_gemm(bn, epi, *ta, *tb, *tc, p, st);
   time_end(e, st);
   e->st.launches++;
   e->st.gemm_launches++;
@@ -794,16 +815,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     }
     GemmParams p = base_params(B, c.vocab_size, H);
     p.out = logits; p.ldo = c.vocab_size; p.softcap = c.final_logit_softcap;
-    const CUtensorMap *ta, *tb;
-    CKR(get_tmap(e, a, lda_rows ? e->ws_batch : e->ws_tokens, H, H, GEMM_BM, &ta));
-    const int bn = B <= 128 ? 128 : 256;
-    CKR(get_tmap(e, e->embed, c.vocab_size, H, H, bn, &tb));
-    time_begin(e, st, 2.0 * B * static_cast<double>(c.vocab_size) * H, 0);
-    int r = launch_gemm(bn, EPI_F32, *ta, *tb, p, st);
-    time_end(e, st);
-    CKR(r);
-    e->st.launches++;
-    e->st.gemm_launches++;
+    CKR(eng_gemm(e, st, B <= 128 ? 128 : 256, EPI_F32, a, H, e->embed, p, lda_rows ? e->ws_batch : e->ws_tokens));
   }
   add_scalar_kernel<<<1, 32, 0, st>>>(cache->t0_dev, S);
   CK(cudaGetLastError());
@@ -1005,7 +1017,10 @@ extern "C" int b2_op_gemm(const void* a, const void* w, void* out, int M, int N,
   p.ldo = (epi == EPI_GLU) ? N / 2 : N;
   p.softcap = softcap;
   p.act = act;
-  return launch_gemm(bn, epi, ta, tb, p, static_cast<cudaStream_t>(stream));
+  p.band_m = pick_band(N, K);
+  CUtensorMap tc = ta;
+  if (epi == EPI_F32 || epi == EPI_RESID) CKR(make_tmap_t(&tc, out, M, N, N, 32, true));
+  return launch_gemm(bn, epi, ta, tb, tc, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b2_op_qkv_rope(const void* a, const void* w, void* q, void* kc, void* vc, int B, int S, int H, int NH,
@@ -1034,7 +1049,7 @@ extern "C" int b2_op_qkv_rope(const void* a, const void* w, void* q, void* kc, v
   p.q_out = static_cast<bf16*>(q); p.ldq = NH * HD;
   p.k_cache = static_cast<bf16*>(kc); p.v_cache = static_cast<bf16*>(vc);
   p.t0_ptr = dt0; p.rope_cos = dc; p.rope_sin = ds;
-  int r = launch_gemm(bn, EPI_QKV_ROPE, ta, tb, p, st);
+  int r = launch_gemm(bn, EPI_QKV_ROPE, ta, tb, ta, p, st);
   cudaError_t se = cudaStreamSynchronize(st);
   cudaFree(dc); cudaFree(ds); cudaFree(dt0);
   if (r == B2_OK && se != cudaSuccess) return fail(B2_ERR_CUDA, "qkv_rope kernel failed: %s", cudaGetErrorString(se));

@@ -4,13 +4,17 @@
 //   W  weights in HF layout [out_features, in_features]   -> UMMA B operand, K-major
 //   (this is the reference's Linear_np: y = x . W^T, llama3.2_model_numpy.py:124-144)
 //
-// One CTA per SM, 192 threads:
+// One CTA per SM, 320 threads:
 //   warp 0    TMA producer: cp.async.bulk.tensor 128B-swizzled {64 x 128} A and {64 x BN} W boxes
 //             into a STAGES-deep shared-memory ring, completion on "full" mbarriers
 //   warp 1    MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
 //             TMEM accumulators; tcgen05.commit releases ring slots / publishes the accumulator
-//   warps 2-5 epilogue: tcgen05.ld (lane = output row) -> fused epilogue -> global stores, overlapped
-//             with the next tile's main loop through the double-buffered accumulator
+//   warps 2-9 epilogue (two warps per TMEM lane quarter, each taking every other column group):
+//             tcgen05.ld (lane = output row) -> fused epilogue -> global memory, overlapped with the
+//             next tile's main loop through the double-buffered accumulator.  fp32 outputs are staged
+//             in 128B-swizzled shared memory and leave through TMA (bulk tensor store, or bulk tensor
+//             reduce-add for the residual stream), so HBM sees full 128-byte lines and the residual
+//             add needs no load.
 //
 // Fused epilogues: plain bf16 / fp32 (+tanh soft-cap, gemma2_model.py:867-870),
 // residual add (llama3.2_model_numpy.py:569,578), RoPE + KV-cache append for the fused QKV weight
@@ -25,9 +29,9 @@ enum GemmEpi : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_QKV_ROPE = 3,
 struct GemmParams {
   int M, N, K;   // K = contraction length seen by A (2*k_wrap in hi/lo "precise" mode)
   int k_wrap;    // W k-coordinate = k % k_wrap
-  int band_m;    // rasterisation: m-blocks per band (W tiles stay hot in L2 inside a band)
-  int split_k;   // >1: K is split across CTAs (skinny decode GEMMs); only EPI_RESID (fp32 atomics) supports it
-  // EPI_BF16 / EPI_F32 / EPI_RESID / EPI_GLU
+  int band_m;    // rasterisation: m-blocks per band (operand tiles stay hot in L2 inside a band)
+  int split_k;   // >1: K is split across CTAs (skinny GEMMs); only EPI_RESID supports it (reduce-add)
+  // EPI_BF16 / EPI_GLU (direct stores); EPI_F32 / EPI_RESID go through the output tensor map
   void* out;
   int ldo;         // row stride of out, in elements
   float softcap;   // EPI_F32: cap * tanh(x / cap) when > 0
@@ -47,15 +51,17 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;   // one 32x32 fp32 slab per epilogue warp
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: alignment
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 };
 
@@ -83,70 +89,71 @@ __device__ __forceinline__ void split_lo(const float (&v)[32], float (&lo)[32]) 
   for (int i = 0; i < 32; ++i) lo[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
 }
 
+// Epilogue of one tile for one warp.  `quarter` = TMEM lane quarter (rows), `half` = which of the two
+// warps sharing that quarter (takes column groups of its parity), `slab` = this warp's 4 KB staging.
 template <int BN, int EPI>
-__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint32_t tacc, int mb, int nb, int quarter,
-                                              int lane) {
-  const int row = mb * GEMM_BM + quarter * 32 + lane;
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtensorMap* tmap_c, uint8_t* slab,
+                                              uint32_t tacc, int mb, int nb, int quarter, int half, int lane) {
+  const int row0 = mb * GEMM_BM + quarter * 32;
+  const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const int col0 = nb * BN;
   const uint32_t trow = tacc + (static_cast<uint32_t>(quarter * 32) << 16);
 
-  if constexpr (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID) {
+  if constexpr (EPI == EPI_F32 || EPI == EPI_RESID) {
+    // registers -> swizzled smem slab (row = lane, 16-byte chunk j at j ^ (lane & 7)) -> TMA store / reduce-add
+    const float inv_cap = p.softcap > 0.f ? 1.0f / p.softcap : 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half; c < BN / 32; c += 2) {
+      const int col = col0 + c * 32;
+      if (col >= p.N) break;
+      uint32_t r[32];
+      tmem_ld32(trow + c * 32, r);
+      tmem_ld_wait();
+      if (EPI == EPI_F32 && p.softcap > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(p.softcap * tanhf(__uint_as_float(r[i]) * inv_cap));
+      }
+      if (lane == 0) tma_store_wait_read<0>();   // the previous bulk store has finished reading the slab
+      __syncwarp();
+      uint8_t* srow = slab + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && row0 < p.M) {
+        if (EPI == EPI_F32) tma_store_2d(tmap_c, slab, col, row0);
+        else tma_reduce_add_2d(tmap_c, slab, col, row0);   // x += acc  (fp32 residual stream)
+        tma_store_commit();
+      }
+    }
+  } else if constexpr (EPI == EPI_BF16) {
+#pragma unroll 1
+    for (int c = half; c < BN / 32; c += 2) {
       const int col = col0 + c * 32;
       if (col >= p.N) break;
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
       uint32_t r[32];
       tmem_ld32(trow + c * 32, r);
       tmem_ld_wait();
+      if (!row_ok) continue;
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-      if (!row_ok) continue;
-      if constexpr (EPI == EPI_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
-        store_bf16x32(o, v);
-        if (p.lo_off) {
-          float lo[32];
-          split_lo(v, lo);
-          store_bf16x32(o + p.lo_off, lo);
-        }
-      } else if constexpr (EPI == EPI_F32) {
-        if (p.softcap > 0.f) {
-          const float inv = 1.0f / p.softcap;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = p.softcap * tanhf(v[i] * inv);
-        }
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) __stcs(o + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-      } else {  // EPI_RESID: x += acc, fp32 residual stream
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
-        if (p.split_k > 1) {
-          float* of = reinterpret_cast<float*>(o);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(of + i, v[i]);
-          continue;
-        }
-        float4 x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = o[i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          x[i].x += v[4 * i];
-          x[i].y += v[4 * i + 1];
-          x[i].z += v[4 * i + 2];
-          x[i].w += v[4 * i + 3];
-          o[i] = x[i];
-        }
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+      store_bf16x32(o, v);
+      if (p.lo_off) {
+        float lo[32];
+        split_lo(v, lo);
+        store_bf16x32(o + p.lo_off, lo);
       }
     }
   } else if constexpr (EPI == EPI_GLU) {
     // W rows are interleaved in 32-row groups: [gate 32j..32j+31 | up 32j..32j+31] -> column chunk 2j is
     // gate, chunk 2j+1 is up, output column = N/2-space (col0/2 + 32j).
 #pragma unroll 1
-    for (int j = 0; j < BN / 64; ++j) {
+    for (int j = half; j < BN / 64; j += 2) {
       const int col = col0 + j * 64;
       if (col >= p.N) break;
       __syncwarp();
@@ -172,14 +179,16 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint32_t tacc
     }
   } else {  // EPI_QKV_ROPE
     const int HD = p.head_dim;
-    const int half_chunks = HD >> 6;  // chunks (of 32 columns) per half head
+    const int half_chunks = HD >> 6;  // 32-column chunks per half head
     const int t0 = *p.t0_ptr;
     const int b = row / p.S, s = row - b * p.S;
     const int pos = t0 + s;
     const float* cosr = p.rope_cos + static_cast<size_t>(pos) * (HD >> 1);
     const float* sinr = p.rope_sin + static_cast<size_t>(pos) * (HD >> 1);
+    // work items: (head hh, half-chunk i); this warp takes the items of its parity
 #pragma unroll 1
-    for (int hh = 0; hh < BN / HD; ++hh) {
+    for (int t = half; t < BN / 64; t += 2) {
+      const int hh = t / half_chunks, i = t - hh * half_chunks;
       const int n0 = col0 + hh * HD;  // first fused-QKV column of this head
       if (n0 >= p.N) break;
       __nv_bfloat16* dst;
@@ -200,47 +209,52 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint32_t tacc
         dst = base + (static_cast<size_t>(b * p.nkv + kvh) * p.Tmax + pos) * HD;
         lo_off = p.kv_lo_off;
       }
-#pragma unroll 1
-      for (int i = 0; i < half_chunks; ++i) {
-        __syncwarp();
-        uint32_t a[32], c[32];
-        const int cl = hh * (HD >> 5) + i;  // chunk holding x1 (first half of the head)
-        tmem_ld32(trow + cl * 32, a);
-        tmem_ld32(trow + (cl + half_chunks) * 32, c);  // matching x2 chunk (second half)
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        float x1[32], x2[32];
-        if (rope) {
-          // q*cos + rotate_half(q)*sin with rotate_half = [-x2, x1]  (llama3.2_model_numpy.py:69-90)
-          const float4* c4 = reinterpret_cast<const float4*>(cosr + i * 32);
-          const float4* s4 = reinterpret_cast<const float4*>(sinr + i * 32);
+      __syncwarp();
+      uint32_t a[32], c[32];
+      const int cl = hh * (HD >> 5) + i;  // chunk holding x1 (first half of the head)
+      tmem_ld32(trow + cl * 32, a);
+      tmem_ld32(trow + (cl + half_chunks) * 32, c);  // matching x2 chunk (second half)
+      float4 cs4[8], sn4[8];
+      if (rope && row_ok) {   // table loads overlap the TMEM load latency
+        const float4* c4 = reinterpret_cast<const float4*>(cosr + i * 32);
+        const float4* s4 = reinterpret_cast<const float4*>(sinr + i * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 cc = __ldg(c4 + j), ss = __ldg(s4 + j);
-            const float cs[4] = {cc.x, cc.y, cc.z, cc.w}, sn[4] = {ss.x, ss.y, ss.z, ss.w};
+        for (int j = 0; j < 8; ++j) {
+          cs4[j] = __ldg(c4 + j);
+          sn4[j] = __ldg(s4 + j);
+        }
+      }
+      __syncwarp();
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float x1[32], x2[32];
+      if (rope) {
+        // q*cos + rotate_half(q)*sin with rotate_half = [-x2, x1]  (llama3.2_model_numpy.py:69-90)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float p1 = __uint_as_float(a[4 * j + e]), p2 = __uint_as_float(c[4 * j + e]);
-              x1[4 * j + e] = p1 * cs[e] - p2 * sn[e];
-              x2[4 * j + e] = p2 * cs[e] + p1 * sn[e];
-            }
-          }
-        } else {
+        for (int j = 0; j < 8; ++j) {
+          const float cs[4] = {cs4[j].x, cs4[j].y, cs4[j].z, cs4[j].w}, sn[4] = {sn4[j].x, sn4[j].y, sn4[j].z, sn4[j].w};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x1[j] = __uint_as_float(a[j]);
-            x2[j] = __uint_as_float(c[j]);
+          for (int e = 0; e < 4; ++e) {
+            const float p1 = __uint_as_float(a[4 * j + e]), p2 = __uint_as_float(c[4 * j + e]);
+            x1[4 * j + e] = p1 * cs[e] - p2 * sn[e];
+            x2[4 * j + e] = p2 * cs[e] + p1 * sn[e];
           }
         }
-        store_bf16x32(dst + i * 32, x1);
-        store_bf16x32(dst + (HD >> 1) + i * 32, x2);
-        if (lo_off) {
-          float lo[32];
-          split_lo(x1, lo);
-          store_bf16x32(dst + lo_off + i * 32, lo);
-          split_lo(x2, lo);
-          store_bf16x32(dst + lo_off + (HD >> 1) + i * 32, lo);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x1[j] = __uint_as_float(a[j]);
+          x2[j] = __uint_as_float(c[j]);
         }
+      }
+      store_bf16x32(dst + i * 32, x1);
+      store_bf16x32(dst + (HD >> 1) + i * 32, x2);
+      if (lo_off) {
+        float lo[32];
+        split_lo(x1, lo);
+        store_bf16x32(dst + lo_off + i * 32, lo);
+        split_lo(x2, lo);
+        store_bf16x32(dst + lo_off + (HD >> 1) + i * 32, lo);
       }
     }
   }
@@ -249,14 +263,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint32_t tacc
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint8_t* sStage = smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES);     // 1024-byte aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -272,13 +287,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (EPI == EPI_F32 || EPI == EPI_RESID) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -351,20 +367,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    const int quarter = warp & 3;
+    const int ew = warp - 2;                 // 0..7
+    const int quarter = warp & 3;            // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
+    const int half = ew >> 2;                // two warps share a quarter; each takes every other column group
+    uint8_t* slab = sStage + ew * 4096;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int mb, nb, kb0;
       tile_coords(tile, mb, nb, kb0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      gemm_epilogue<BN, EPI>(p, tmem_base + acc * BN, mb, nb, quarter, lane);
+      gemm_epilogue<BN, EPI>(p, &tmap_c, slab, tmem_base + acc * BN, mb, nb, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if ((EPI == EPI_F32 || EPI == EPI_RESID) && lane == 0) tma_store_wait_all();   // bulk stores drained before exit
   }
   tc_fence_before();
   __syncthreads();
