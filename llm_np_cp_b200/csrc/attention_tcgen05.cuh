@@ -48,76 +48,166 @@ struct AttnCfg {
 
 
 // ---- per-row softmax pieces (thread = q row).  Mask test: column cc is valid iff (unsigned)(cc - lo) < span.
-template <int SCH, bool MASK>
-__device__ __forceinline__ float att_row_max(uint32_t tS_row, int lo, unsigned span) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < SCH; ++c) {
-    uint32_t sr[32];
-    tmem_ld32(tS_row + c * 32, sr);
-    tmem_ld_wait();
-    const int rel = c * 32 - lo;
+// TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is processed
+// (tcgen05.wait::ld waits for every outstanding load, so it is placed after the compute of chunk c).
+template <bool MASK>
+__device__ __forceinline__ void att_max32(const uint32_t (&sr)[32], int rel, unsigned span, float (&m)[4]) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float v0 = __uint_as_float(sr[i]), v1 = __uint_as_float(sr[i + 1]);
-      float v2 = __uint_as_float(sr[i + 2]), v3 = __uint_as_float(sr[i + 3]);
-      if (MASK) {
-        v0 = static_cast<unsigned>(rel + i) < span ? v0 : -INFINITY;
-        v1 = static_cast<unsigned>(rel + i + 1) < span ? v1 : -INFINITY;
-        v2 = static_cast<unsigned>(rel + i + 2) < span ? v2 : -INFINITY;
-        v3 = static_cast<unsigned>(rel + i + 3) < span ? v3 : -INFINITY;
-      }
-      m0 = fmaxf(m0, v0);
-      m1 = fmaxf(m1, v1);
-      m2 = fmaxf(m2, v2);
-      m3 = fmaxf(m3, v3);
+  for (int i = 0; i < 32; i += 4) {
+    float v0 = __uint_as_float(sr[i]), v1 = __uint_as_float(sr[i + 1]);
+    float v2 = __uint_as_float(sr[i + 2]), v3 = __uint_as_float(sr[i + 3]);
+    if (MASK) {
+      v0 = static_cast<unsigned>(rel + i) < span ? v0 : -INFINITY;
+      v1 = static_cast<unsigned>(rel + i + 1) < span ? v1 : -INFINITY;
+      v2 = static_cast<unsigned>(rel + i + 2) < span ? v2 : -INFINITY;
+      v3 = static_cast<unsigned>(rel + i + 3) < span ? v3 : -INFINITY;
     }
+    m[0] = fmaxf(m[0], v0);
+    m[1] = fmaxf(m[1], v1);
+    m[2] = fmaxf(m[2], v2);
+    m[3] = fmaxf(m[3], v3);
   }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// P = exp2(x - m) with x = s*sl2 (or the soft-capped score in log2 units); bf16 P -> 128B-swizzled smem rows
-// (the K-major A operand of P.V); returns the row sum of the fp32 probabilities.
+template <int SCH, bool MASK>
+__device__ __forceinline__ float att_row_max(uint32_t tS_row, int lo, unsigned span) {
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  uint32_t buf[2][32];
+  tmem_ld32(tS_row, buf[0]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < SCH; ++c) {
+    if (c + 1 < SCH) tmem_ld32(tS_row + (c + 1) * 32, buf[(c + 1) & 1]);
+    att_max32<MASK>(buf[c & 1], c * 32 - lo, span, m);
+    if (c + 1 < SCH) tmem_ld_wait();
+  }
+  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+}
+
+// one 32-column chunk: P = exp2(x - m) with x = s*sl2 (or the soft-capped score in log2 units);
+// bf16 P -> 128B-swizzled smem row (the K-major A operand of P.V); accumulates the fp32 row sum.
+template <bool MASK, bool CAP>
+__device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8_t* sP, int r, float sl2, float m_safe,
+                                          float cap_in, float cap_out, int lo, unsigned span, float (&sum)[4]) {
+  const int rel = c * 32 - lo;
+  float e[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float sv = __uint_as_float(sr[i]);
+    float x;
+    if (CAP) x = fmaf(fast_tanh(sv * cap_in), cap_out, -m_safe);   // cap*log2e*tanh(s*scale/cap) - m
+    else x = fmaf(sv, sl2, -m_safe);
+    if (MASK) x = static_cast<unsigned>(rel + i) < span ? x : -INFINITY;
+    e[i] = fast_exp2(x);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    sum[0] += e[i];
+    sum[1] += e[i + 1];
+    sum[2] += e[i + 2];
+    sum[3] += e[i + 3];
+  }
+  uint8_t* prow = sP + (c >> 1) * (ATT_BM * 128) + r * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16(e[8 * i + 0], e[8 * i + 1]);
+    u.y = pack_bf16(e[8 * i + 2], e[8 * i + 3]);
+    u.z = pack_bf16(e[8 * i + 4], e[8 * i + 5]);
+    u.w = pack_bf16(e[8 * i + 6], e[8 * i + 7]);
+    const int chunk16 = (c & 1) * 4 + i;
+    *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
+  }
+}
+
 template <int SCH, bool MASK, bool CAP>
 __device__ __forceinline__ float att_row_exp(uint32_t tS_row, uint8_t* sP, int r, float sl2, float m_safe, float cap_in,
                                              float cap_out, int lo, unsigned span) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 1
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t buf[2][32];
+  tmem_ld32(tS_row, buf[0]);
+  tmem_ld_wait();
+#pragma unroll
   for (int c = 0; c < SCH; ++c) {
-    uint32_t sr[32];
-    tmem_ld32(tS_row + c * 32, sr);
-    tmem_ld_wait();
-    const int rel = c * 32 - lo;
-    float e[32];
+    if (c + 1 < SCH) tmem_ld32(tS_row + (c + 1) * 32, buf[(c + 1) & 1]);
+    att_exp32<MASK, CAP>(buf[c & 1], c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum);
+    if (c + 1 < SCH) tmem_ld_wait();
+  }
+  return (sum[0] + sum[1]) + (sum[2] + sum[3]);
+}
+
+// One kv tile of the online softmax for one q row: pass 1 (row max), lazy O rescale, pass 2 (P, row sum).
+// S lives at tS_row, O at tO_row (TMEM, this thread's lane), P goes to sP (smem).
+template <int SCH, int OCH>
+__device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_row, uint8_t* sP, int r, bool need_mask,
+                                                 int lo, unsigned span, bool cap, float sl2, float cap_in, float cap_out,
+                                                 float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity) {
+  constexpr float TAU = 8.0f;   // lazy-rescale threshold (log2 units): P stays <= 2^8
+  const float mx = need_mask ? att_row_max<SCH, true>(tS_row, lo, span) : att_row_max<SCH, false>(tS_row, lo, span);
+  float m_tile = mx;                               // -> log2 domain, after the optional soft-cap
+  if (mx != -INFINITY) m_tile = cap ? cap_out * fast_tanh(mx * cap_in) : mx * sl2;
+  float alpha = 1.0f;
+  if (m_tile > m_used + TAU || m_used == -INFINITY) {
+    if (m_used != -INFINITY) alpha = fast_exp2(m_used - m_tile);
+    if (m_tile != -INFINITY) m_used = m_tile;
+  }
+  if (have_o) {
+    mbar_wait(bar_o, o_parity);                    // previous P.V finished: O readable, sP reusable
+    tc_fence_after();
+    if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+      l *= alpha;
+#pragma unroll 1
+      for (int c = 0; c < OCH; ++c) {
+        uint32_t orr[32];
+        tmem_ld32(tO_row + c * 32, orr);
+        tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float sv = __uint_as_float(sr[i]);
-      float x;
-      if (CAP) x = fmaf(fast_tanh(sv * cap_in), cap_out, -m_safe);   // cap*log2e*tanh(s*scale/cap) - m
-      else x = fmaf(sv, sl2, -m_safe);
-      if (MASK) x = static_cast<unsigned>(rel + i) < span ? x : -INFINITY;
-      e[i] = fast_exp2(x);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      s0 += e[i];
-      s1 += e[i + 1];
-      s2 += e[i + 2];
-      s3 += e[i + 3];
-    }
-    uint8_t* prow = sP + (c >> 1) * (ATT_BM * 128) + r * 128;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(e[8 * i + 0], e[8 * i + 1]);
-      u.y = pack_bf16(e[8 * i + 2], e[8 * i + 3]);
-      u.z = pack_bf16(e[8 * i + 4], e[8 * i + 5]);
-      u.w = pack_bf16(e[8 * i + 6], e[8 * i + 7]);
-      const int chunk16 = (c & 1) * 4 + i;
-      *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
+        for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+        tmem_st32(tO_row + c * 32, orr);
+      }
+      tmem_st_wait();
     }
   }
-  return (s0 + s1) + (s2 + s3);
+  const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
+  float lsum;
+  if (cap) {
+    lsum = need_mask ? att_row_exp<SCH, true, true>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
+                     : att_row_exp<SCH, false, true>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
+  } else {
+    lsum = need_mask ? att_row_exp<SCH, true, false>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
+                     : att_row_exp<SCH, false, false>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
+  }
+  l += lsum;
+}
+
+// O / l -> bf16 -> out row (the reference's transpose+reshape, llama3.2_model_numpy.py:509-511)
+template <int OCH>
+__device__ __forceinline__ void att_store_out(uint32_t tO_row, bool have_o, float l, bool row_ok, __nv_bfloat16* orow) {
+  const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+#pragma unroll 1
+  for (int c = 0; c < OCH; ++c) {
+    __syncwarp();
+    uint32_t orr[32];
+    if (have_o) {
+      tmem_ld32(tO_row + c * 32, orr);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) orr[i] = 0u;
+    }
+    if (row_ok) {
+      uint4* d = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(orr[8 * i + 0]) * inv_l, __uint_as_float(orr[8 * i + 1]) * inv_l);
+        u.y = pack_bf16(__uint_as_float(orr[8 * i + 2]) * inv_l, __uint_as_float(orr[8 * i + 3]) * inv_l);
+        u.z = pack_bf16(__uint_as_float(orr[8 * i + 4]) * inv_l, __uint_as_float(orr[8 * i + 5]) * inv_l);
+        u.w = pack_bf16(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
+        d[i] = u;
+      }
+    }
+  }
 }
 
 template <int HD>
@@ -129,7 +219,6 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   constexpr int HB = HD / 64;        // 64-column (128-byte) blocks per head
   constexpr int SCH = BNKV / 32;     // 32-column chunks of S per row
   constexpr int OCH = HD / 32;       // 32-column chunks of O per row
-  constexpr float TAU = 8.0f;        // lazy-rescale threshold (log2 units)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -288,88 +377,276 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const unsigned span = hi > lo ? static_cast<unsigned>(hi - lo) : 0u;
       mbar_wait(bar_s, it & 1);
       tc_fence_after();
-      // ---- pass 1: row max of the raw scores ----
-      const float mx = need_mask ? att_row_max<SCH, true>(tS + lane_off, lo, span)
-                                 : att_row_max<SCH, false>(tS + lane_off, lo, span);
-      float m_tile = mx;                            // -> log2 domain, after the optional soft-cap
-      if (mx != -INFINITY) {
-        if (cap) m_tile = cap_out * fast_tanh(mx * cap_in);
-        else m_tile = mx * sl2;
-      }
-      // ---- lazy rescale of O / l ----
-      float alpha = 1.0f;
-      if (m_tile > m_used + TAU || m_used == -INFINITY) {
-        if (m_used != -INFINITY) alpha = fast_exp2(m_used - m_tile);
-        if (m_tile != -INFINITY) m_used = m_tile;
-      }
-      if (it > 0) {
-        mbar_wait(bar_o, (it - 1) & 1);             // previous P.V finished: O readable, sP reusable
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          l *= alpha;
-#pragma unroll 1
-          for (int c = 0; c < OCH; ++c) {
-            uint32_t orr[32];
-            tmem_ld32(tO + lane_off + c * 32, orr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-            tmem_st32(tO + lane_off + c * 32, orr);
-          }
-          tmem_st_wait();
-        }
-      }
-      // ---- pass 2: P = exp2(s - m), row sum, bf16 P -> swizzled smem (K-major SW128 A operand) ----
-      const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
-      float lsum;
-      if (cap) {
-        lsum = need_mask ? att_row_exp<SCH, true, true>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
-                         : att_row_exp<SCH, false, true>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
-      } else {
-        lsum = need_mask ? att_row_exp<SCH, true, false>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
-                         : att_row_exp<SCH, false, false>(tS + lane_off, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
-      }
-      l += lsum;
+      att_softmax_tile<SCH, OCH>(tS + lane_off, tO + lane_off, sP, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l,
+                                 it > 0, bar_o, (it - 1) & 1);
       fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the MMA
       tc_fence_before();
       mbar_arrive(bar_p);
     }
-    // ---- epilogue: O / l -> bf16 -> [B*S, NH*HD] (the reference's transpose+reshape, :509-511) ----
+    // ---- epilogue: O / l -> bf16 -> [B*S, NH*HD] ----
     if (n_tiles > 0) {
       mbar_wait(bar_o, (n_tiles - 1) & 1);
       tc_fence_after();
     }
-    const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
-    const bool row_ok = (q0 + r) < p.S;
-    __nv_bfloat16* orow = p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD;
-#pragma unroll 1
-    for (int c = 0; c < OCH; ++c) {
-      __syncwarp();
-      uint32_t orr[32];
-      if (n_tiles > 0) {
-        tmem_ld32(tO + lane_off + c * 32, orr);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) orr[i] = 0u;
-      }
-      if (row_ok) {
-        uint4* d = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(orr[8 * i + 0]) * inv_l, __uint_as_float(orr[8 * i + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(orr[8 * i + 2]) * inv_l, __uint_as_float(orr[8 * i + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(orr[8 * i + 4]) * inv_l, __uint_as_float(orr[8 * i + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
-          d[i] = u;
-        }
-      }
-    }
+    att_store_out<OCH>(tO + lane_off, n_tiles > 0, l, (q0 + r) < p.S,
+                       p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined prefill kernel (head_dim 64 / 128): one CTA owns TWO consecutive 128-row q tiles of one
+// (batch, head) and ping-pongs them through the tensor core, so the S = Q.K^T of one tile and the P.V of
+// the other run while the softmax warps of either tile are busy.  1 CTA / SM, 320 threads:
+//   warps 0-3   softmax / correction / epilogue of q tile 0        (thread = q row = TMEM lane)
+//   warps 4-7   same for q tile 1
+//   warp  8     TMA producer: both Q tiles once, K/V tiles through a 3-stage ring (shared by both q tiles)
+//   warp  9     tcgen05.mma issuer.  Per kv tile j and q tile g:   wait P_g(j) -> O_g += P_g.V_j ->
+//               S_g(j+1) = Q_g.K_(j+1)^T, i.e. the next scores of tile g are issued as soon as its softmax
+//               has consumed the previous ones.
+// TMEM: S0 | S1 | O0 | O1  (2*BNKV + 2*HD <= 512 columns).
+// ---------------------------------------------------------------------------------------------
+constexpr int ATT2_THREADS = 320;
+
+template <int HD>
+struct Attn2Cfg {
+  static constexpr int BNKV = (HD == 64) ? 128 : 64;
+  static constexpr int KV_STAGES = 3;
+  static constexpr int Q_BYTES = ATT_BM * HD * 2;        // one q tile
+  static constexpr int KV_BYTES = BNKV * HD * 2;         // one K or V tile
+  static constexpr int P_BYTES = ATT_BM * BNKV * 2;      // one P tile
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(2 * BNKV + 2 * HD <= 512, "TMEM budget");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                         const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = Attn2Cfg<HD>;
+  constexpr int BNKV = Cfg::BNKV;
+  constexpr int ST = Cfg::KV_STAGES;
+  constexpr int HB = HD / 64;
+  constexpr int SCH = BNKV / 32;
+  constexpr int OCH = HD / 32;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                   // [2][128 x HD]
+  uint8_t* sK = sQ + 2 * Cfg::Q_BYTES;                  // [ST]
+  uint8_t* sV = sK + ST * Cfg::KV_BYTES;                // [ST]
+  uint8_t* sP = sV + ST * Cfg::KV_BYTES;                // [2][128 x BNKV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
+  uint64_t* bar_q = bars;            // 1
+  uint64_t* k_full = bars + 1;       // [ST]
+  uint64_t* v_full = bars + 4;       // [ST]
+  uint64_t* kv_empty = bars + 7;     // [ST]
+  uint64_t* s_full = bars + 10;      // [2]
+  uint64_t* p_ready = bars + 12;     // [2]
+  uint64_t* o_done = bars + 14;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
+  const int n_pairs = (n_qt + 1) / 2;
+  const int pi = n_pairs - 1 - static_cast<int>(blockIdx.x);    // heaviest pairs first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.NH / p.NKV);
+  const int t0 = *p.t0_ptr;
+  const int T = t0 + p.S;
+  // per q tile g: rows [q0g, q0g+128), kv tiles [jb[g], je[g])
+  int q0g[2], jb[2], je[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    q0g[g] = (2 * pi + g) * ATT_BM;
+    if (2 * pi + g >= n_qt) {
+      jb[g] = je[g] = 0;          // tile does not exist (odd tile count)
+    } else {
+      int kv_end = T;
+      if (p.causal) kv_end = min(T, t0 + q0g[g] + ATT_BM);
+      int kv_begin = 0;
+      if (p.window > 0) kv_begin = max(0, t0 + q0g[g] - p.window + 1);
+      jb[g] = kv_begin / BNKV;
+      je[g] = (kv_end + BNKV - 1) / BNKV;
+    }
+  }
+  const int j_lo = (je[1] > jb[1]) ? min(jb[0], jb[1]) : jb[0];
+  const int j_hi = max(je[0], je[1]);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_ready[g], 128);
+      mbar_init(&o_done[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d(sQ + g * Cfg::Q_BYTES + hb * (ATT_BM * 128), &tmap_q, bar_q, h * HD + hb * 64,
+                      b * p.S + q0g[g], kEvictFirst);
+      const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = j_lo; j < j_hi; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&k_full[stage], Cfg::KV_BYTES);
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d(sK + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[stage], hb * 64,
+                      kv_row0 + j * BNKV, kEvictLast);
+        mbar_expect_tx(&v_full[stage], Cfg::KV_BYTES);
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d(sV + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_v, &v_full[stage], hb * 64,
+                      kv_row0 + j * BNKV, kEvictLast);
+        if (++stage == ST) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // P (K-major) x V (MN-major)
+      auto issue_s = [&](int g, int stage) {    // S_g = Q_g . K^T
+        const uint32_t q_addr = smem_u32(sQ + g * Cfg::Q_BYTES);
+        const uint32_t k_addr = smem_u32(sK + stage * Cfg::KV_BYTES);
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_base + g * BNKV, umma_smem_desc(q_addr + hb * (ATT_BM * 128) + k * 32, 16, 1024),
+                         umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024), idesc_s, (hb | k) != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, int stage, bool first) {   // O_g (+)= P_g . V
+        const uint32_t p_addr = smem_u32(sP + g * Cfg::P_BYTES);
+        const uint32_t v_addr = smem_u32(sV + stage * Cfg::KV_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BNKV / 16; ++kk)
+          umma_bf16_ss(tmem_base + 2 * BNKV + g * HD,
+                       umma_smem_desc(p_addr + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
+                       umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (!first || kk != 0) ? 1u : 0u);
+        umma_commit(&o_done[g]);
+      };
+      mbar_wait(bar_q, 0);
+      int stage = 0;                       // ring slot of kv tile j
+      uint32_t phase = 0;
+      uint32_t np[2] = {0, 0};             // tiles whose P has been consumed, per q tile (parity of p_ready)
+      if (j_lo < j_hi) {
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (j_lo >= jb[g] && j_lo < je[g]) issue_s(g, 0);
+      }
+      for (int j = j_lo; j < j_hi; ++j) {
+        const int nstage = (stage + 1 == ST) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == ST) ? (phase ^ 1) : phase;
+        bool v_ready = false, k_next_ready = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (j >= jb[g] && j < je[g]) {
+            mbar_wait(&p_ready[g], np[g] & 1);          // softmax of (g, j) done: P_g in smem, S_g free
+            if (!v_ready) {
+              mbar_wait(&v_full[stage], phase);
+              v_ready = true;
+            }
+            tc_fence_after();
+            issue_pv(g, stage, np[g] == 0);
+            ++np[g];
+          }
+          if (j + 1 >= jb[g] && j + 1 < je[g]) {        // next scores of this q tile
+            if (!k_next_ready) {
+              mbar_wait(&k_full[nstage], nphase);
+              k_next_ready = true;
+            }
+            tc_fence_after();
+            issue_s(g, nstage);
+          }
+        }
+        umma_commit(&kv_empty[stage]);                  // every MMA reading K_j / V_j has been issued
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ------------------------------ softmax / correction / epilogue (8 warps, 2 q tiles) ------------------------------
+    const int g = warp >> 2;                         // q tile of this warp
+    const int r = (warp & 3) * 32 + lane;            // row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS_row = tmem_base + g * BNKV + lane_off;
+    const uint32_t tO_row = tmem_base + 2 * BNKV + g * HD + lane_off;
+    uint8_t* sPg = sP + g * Cfg::P_BYTES;
+    const int q0 = q0g[g];
+    const int qpos = t0 + q0 + r;
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = p.scale * LOG2E;
+    const bool cap = p.softcap > 0.f;
+    const float cap_in = cap ? p.scale / p.softcap : 0.f, cap_out = p.softcap * LOG2E;
+    float m_used = -INFINITY, l = 0.f;
+    const int n_tiles = je[g] - jb[g];
+    for (int it = 0; it < n_tiles; ++it) {
+      const int kv0 = (jb[g] + it) * BNKV;
+      const bool need_mask = (p.causal && kv0 + BNKV - 1 > t0 + q0) || (kv0 + BNKV > T) ||
+                             (p.window > 0 && kv0 < t0 + q0 + ATT_BM - p.window);
+      int lo = 0, hi = BNKV;
+      if (need_mask) {
+        int last = T - 1;
+        if (p.causal) last = min(last, qpos);
+        hi = min(BNKV, last - kv0 + 1);
+        if (p.window > 0) lo = max(0, qpos - p.window + 1 - kv0);
+      }
+      const unsigned span = hi > lo ? static_cast<unsigned>(hi - lo) : 0u;
+      mbar_wait(&s_full[g], it & 1);
+      tc_fence_after();
+      att_softmax_tile<SCH, OCH>(tS_row, tO_row, sPg, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l, it > 0,
+                                 &o_done[g], (it - 1) & 1);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_ready[g]);
+    }
+    if (n_tiles > 0) {
+      mbar_wait(&o_done[g], (n_tiles - 1) & 1);
+      tc_fence_after();
+    }
+    if (2 * pi + g < n_qt)
+      att_store_out<OCH>(tO_row, n_tiles > 0, l, (q0 + r) < p.S, p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -208,17 +208,40 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return B2_OK;
 }
 
+template <int HD>
+static int launch_attn_pair_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                              cudaStream_t st) {
+  auto kern = attn_prefill_pair_kernel<HD>;
+  static bool attr[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || !attr[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<HD>::SMEM_BYTES));
+    if (dev < 16) attr[dev] = true;
+  }
+  const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
+  dim3 grid((n_qt + 1) / 2, p.NH, p.B);
+  kern<<<grid, ATT2_THREADS, Attn2Cfg<HD>::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+
+// prefill attention dispatch: the pipelined two-q-tile kernel for head_dim 64/128 (unless B2_ATTN_SINGLE is set
+// or the sequence fits one q tile), the single-tile kernel otherwise (head_dim 256: TMEM/smem budget).
 static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, const AttnParams& p_in, int HD,
                         cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   AttnParams p = p_in;
   if (const char* ev = getenv("B2_V_LBO")) p.v_lbo = atoi(ev);   // bring-up knobs for the MN-major V descriptor
   if (const char* ev = getenv("B2_V_SBO")) p.v_sbo = atoi(ev);
+  static const bool force_single = getenv("B2_ATTN_SINGLE") != nullptr;
+  const bool pair = !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
   const uint64_t kv_rows = static_cast<uint64_t>(p.B) * p.NKV * p.Tmax;
-  const int bnkv = HD <= 128 ? 128 : 64;
+  const int bnkv = pair ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64);
   CKR(make_tmap(&tq, q, static_cast<uint64_t>(p.B) * p.S, static_cast<uint64_t>(p.NH) * HD, ldq, ATT_BM));
   CKR(make_tmap(&tk, kc, kv_rows, HD, HD, bnkv));
   CKR(make_tmap(&tv, vc, kv_rows, HD, HD, bnkv));
+  if (pair) return HD == 64 ? launch_attn_pair_t<64>(tq, tk, tv, p, st) : launch_attn_pair_t<128>(tq, tk, tv, p, st);
   if (HD == 64) return launch_attn_t<64>(tq, tk, tv, p, st);
   if (HD == 128) return launch_attn_t<128>(tq, tk, tv, p, st);
   if (HD == 256) return launch_attn_t<256>(tq, tk, tv, p, st);
