@@ -69,21 +69,6 @@ __device__ __forceinline__ void att_max32(const uint32_t (&sr)[32], int rel, uns
   }
 }
 
-template <int SCH, bool MASK>
-__device__ __forceinline__ float att_row_max(uint32_t tS_row, int lo, unsigned span) {
-  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  uint32_t buf[2][32];
-  tmem_ld32(tS_row, buf[0]);
-  tmem_ld_wait();
-#pragma unroll
-  for (int c = 0; c < SCH; ++c) {
-    if (c + 1 < SCH) tmem_ld32(tS_row + (c + 1) * 32, buf[(c + 1) & 1]);
-    att_max32<MASK>(buf[c & 1], c * 32 - lo, span, m);
-    if (c + 1 < SCH) tmem_ld_wait();
-  }
-  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-}
-
 // one 32-column chunk: P = exp2(x - m) with x = s*sl2 (or the soft-capped score in log2 units);
 // bf16 P -> 128B-swizzled smem row (the K-major A operand of P.V); accumulates the fp32 row sum.
 template <bool MASK, bool CAP>
@@ -120,30 +105,42 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
   }
 }
 
+// One kv tile of the online softmax for one q row, SINGLE pass over TMEM: the whole S row (SCH*32 fp32) is read
+// into registers once (TMEM read bandwidth, not MUFU, is the first limit of a two-pass scheme), S is handed
+// back to the tensor core immediately (bar_sfree), then max -> lazy O rescale -> exp2 / row sum / bf16 P.
+// S lives at tS_row, O at tO_row (TMEM, this thread's lane), P goes to sP (smem, 128B-swizzled rows).
 template <int SCH, bool MASK, bool CAP>
-__device__ __forceinline__ float att_row_exp(uint32_t tS_row, uint8_t* sP, int r, float sl2, float m_safe, float cap_in,
-                                             float cap_out, int lo, unsigned span) {
+__device__ __forceinline__ float att_exp_regs(uint32_t (&x)[SCH][32], uint8_t* sP, int r, float sl2, float m_safe,
+                                              float cap_in, float cap_out, int lo, unsigned span) {
   float sum[4] = {0.f, 0.f, 0.f, 0.f};
-  uint32_t buf[2][32];
-  tmem_ld32(tS_row, buf[0]);
-  tmem_ld_wait();
 #pragma unroll
-  for (int c = 0; c < SCH; ++c) {
-    if (c + 1 < SCH) tmem_ld32(tS_row + (c + 1) * 32, buf[(c + 1) & 1]);
-    att_exp32<MASK, CAP>(buf[c & 1], c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum);
-    if (c + 1 < SCH) tmem_ld_wait();
-  }
+  for (int c = 0; c < SCH; ++c) att_exp32<MASK, CAP>(x[c], c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum);
   return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
-// One kv tile of the online softmax for one q row: pass 1 (row max), lazy O rescale, pass 2 (P, row sum).
-// S lives at tS_row, O at tO_row (TMEM, this thread's lane), P goes to sP (smem).
 template <int SCH, int OCH>
 __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_row, uint8_t* sP, int r, bool need_mask,
                                                  int lo, unsigned span, bool cap, float sl2, float cap_in, float cap_out,
-                                                 float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity) {
+                                                 float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity,
+                                                 uint64_t* bar_sfree) {
   constexpr float TAU = 8.0f;   // lazy-rescale threshold (log2 units): P stays <= 2^8
-  const float mx = need_mask ? att_row_max<SCH, true>(tS_row, lo, span) : att_row_max<SCH, false>(tS_row, lo, span);
+  uint32_t x[SCH][32];
+#pragma unroll
+  for (int c = 0; c < SCH; ++c) tmem_ld32(tS_row + c * 32, x[c]);
+  tmem_ld_wait();
+  if (bar_sfree) {              // scores are in registers: the tensor core may overwrite S
+    tc_fence_before();
+    mbar_arrive(bar_sfree);
+  }
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  if (need_mask) {
+#pragma unroll
+    for (int c = 0; c < SCH; ++c) att_max32<true>(x[c], c * 32 - lo, span, m);
+  } else {
+#pragma unroll
+    for (int c = 0; c < SCH; ++c) att_max32<false>(x[c], 0, 0u, m);
+  }
+  const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
   float m_tile = mx;                               // -> log2 domain, after the optional soft-cap
   if (mx != -INFINITY) m_tile = cap ? cap_out * fast_tanh(mx * cap_in) : mx * sl2;
   float alpha = 1.0f;
@@ -171,11 +168,11 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
   const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
   float lsum;
   if (cap) {
-    lsum = need_mask ? att_row_exp<SCH, true, true>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
-                     : att_row_exp<SCH, false, true>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
+    lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
+                     : att_exp_regs<SCH, false, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
   } else {
-    lsum = need_mask ? att_row_exp<SCH, true, false>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
-                     : att_row_exp<SCH, false, false>(tS_row, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
+    lsum = need_mask ? att_exp_regs<SCH, true, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
+                     : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
   }
   l += lsum;
 }
@@ -211,7 +208,7 @@ __device__ __forceinline__ void att_store_out(uint32_t tO_row, bool have_o, floa
 }
 
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, (HD == 64) ? 2 : 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = AttnCfg<HD>;
@@ -378,7 +375,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(bar_s, it & 1);
       tc_fence_after();
       att_softmax_tile<SCH, OCH>(tS + lane_off, tO + lane_off, sP, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l,
-                                 it > 0, bar_o, (it - 1) & 1);
+                                 it > 0, bar_o, (it - 1) & 1, nullptr);
       fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the MMA
       tc_fence_before();
       mbar_arrive(bar_p);
@@ -401,17 +398,21 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
 // ---------------------------------------------------------------------------------------------
 // Pipelined prefill kernel (head_dim 64 / 128): one CTA owns TWO consecutive 128-row q tiles of one
-// (batch, head) and ping-pongs them through the tensor core, so the S = Q.K^T of one tile and the P.V of
-// the other run while the softmax warps of either tile are busy.  1 CTA / SM, 320 threads:
+// (batch, head) and ping-pongs them through the tensor core.  1 CTA / SM, 384 threads = 3 warpgroups:
 //   warps 0-3   softmax / correction / epilogue of q tile 0        (thread = q row = TMEM lane)
 //   warps 4-7   same for q tile 1
 //   warp  8     TMA producer: both Q tiles once, K/V tiles through a 3-stage ring (shared by both q tiles)
-//   warp  9     tcgen05.mma issuer.  Per kv tile j and q tile g:   wait P_g(j) -> O_g += P_g.V_j ->
-//               S_g(j+1) = Q_g.K_(j+1)^T, i.e. the next scores of tile g are issued as soon as its softmax
-//               has consumed the previous ones.
+//   warp  9     tcgen05.mma issuer (warps 10-11 idle; they only complete the third warpgroup)
+// Register budget is moved with setmaxnreg: the softmax warpgroups hold a whole S row (128 fp32) in registers
+// so TMEM is read once per score; the producer/MMA warpgroup gives its registers away.
+// Per kv tile j and q tile g the MMA warp issues, in this order:
+//     wait S_g(j) consumed  -> S_g(j+1) = Q_g.K_(j+1)^T        (for g = 0, 1)
+//     wait P_g(j) written   -> O_g     += P_g(j).V_j           (for g = 0, 1)
+// so the next scores are already in TMEM when a q tile's softmax warps finish the current ones, and P.V of
+// one q tile overlaps the exponentials of the other.
 // TMEM: S0 | S1 | O0 | O1  (2*BNKV + 2*HD <= 512 columns).
 // ---------------------------------------------------------------------------------------------
-constexpr int ATT2_THREADS = 320;
+constexpr int ATT2_THREADS = 384;
 
 template <int HD>
 struct Attn2Cfg {
@@ -448,10 +449,11 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   uint64_t* k_full = bars + 1;       // [ST]
   uint64_t* v_full = bars + 4;       // [ST]
   uint64_t* kv_empty = bars + 7;     // [ST]
-  uint64_t* s_full = bars + 10;      // [2]
-  uint64_t* p_ready = bars + 12;     // [2]
-  uint64_t* o_done = bars + 14;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s_full = bars + 10;      // [2]  S_g written by the tensor core
+  uint64_t* s_free = bars + 12;      // [2]  S_g copied to registers by all 128 softmax threads
+  uint64_t* p_ready = bars + 14;     // [2]  P_g written to smem by all 128 softmax threads
+  uint64_t* o_done = bars + 16;      // [2]  O_g += P_g.V finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
@@ -492,6 +494,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 128);
       mbar_init(&p_ready[g], 128);
       mbar_init(&o_done[g], 1);
     }
@@ -503,106 +506,118 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    // ------------------------------ TMA producer ------------------------------
-    if (elect_one()) {
-      mbar_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-#pragma unroll
-        for (int hb = 0; hb < HB; ++hb)
-          tma_load_2d(sQ + g * Cfg::Q_BYTES + hb * (ATT_BM * 128), &tmap_q, bar_q, h * HD + hb * 64,
-                      b * p.S + q0g[g], kEvictFirst);
-      const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = j_lo; j < j_hi; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_expect_tx(&k_full[stage], Cfg::KV_BYTES);
-#pragma unroll
-        for (int hb = 0; hb < HB; ++hb)
-          tma_load_2d(sK + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[stage], hb * 64,
-                      kv_row0 + j * BNKV, kEvictLast);
-        mbar_expect_tx(&v_full[stage], Cfg::KV_BYTES);
-#pragma unroll
-        for (int hb = 0; hb < HB; ++hb)
-          tma_load_2d(sV + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_v, &v_full[stage], hb * 64,
-                      kv_row0 + j * BNKV, kEvictLast);
-        if (++stage == ST) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // P (K-major) x V (MN-major)
-      auto issue_s = [&](int g, int stage) {    // S_g = Q_g . K^T
-        const uint32_t q_addr = smem_u32(sQ + g * Cfg::Q_BYTES);
-        const uint32_t k_addr = smem_u32(sK + stage * Cfg::KV_BYTES);
-#pragma unroll
-        for (int hb = 0; hb < HB; ++hb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + g * BNKV, umma_smem_desc(q_addr + hb * (ATT_BM * 128) + k * 32, 16, 1024),
-                         umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024), idesc_s, (hb | k) != 0 ? 1u : 0u);
-        umma_commit(&s_full[g]);
-      };
-      auto issue_pv = [&](int g, int stage, bool first) {   // O_g (+)= P_g . V
-        const uint32_t p_addr = smem_u32(sP + g * Cfg::P_BYTES);
-        const uint32_t v_addr = smem_u32(sV + stage * Cfg::KV_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < BNKV / 16; ++kk)
-          umma_bf16_ss(tmem_base + 2 * BNKV + g * HD,
-                       umma_smem_desc(p_addr + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
-                       umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (!first || kk != 0) ? 1u : 0u);
-        umma_commit(&o_done[g]);
-      };
-      mbar_wait(bar_q, 0);
-      int stage = 0;                       // ring slot of kv tile j
-      uint32_t phase = 0;
-      uint32_t np[2] = {0, 0};             // tiles whose P has been consumed, per q tile (parity of p_ready)
-      if (j_lo < j_hi) {
-        mbar_wait(&k_full[0], 0);
-        tc_fence_after();
+  if (warp >= 8) {
+    setmaxnreg_dec<40>();
+    if (warp == 8) {
+      // ------------------------------ TMA producer ------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
 #pragma unroll
         for (int g = 0; g < 2; ++g)
-          if (j_lo >= jb[g] && j_lo < je[g]) issue_s(g, 0);
-      }
-      for (int j = j_lo; j < j_hi; ++j) {
-        const int nstage = (stage + 1 == ST) ? 0 : stage + 1;
-        const uint32_t nphase = (stage + 1 == ST) ? (phase ^ 1) : phase;
-        bool v_ready = false, k_next_ready = false;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (j >= jb[g] && j < je[g]) {
-            mbar_wait(&p_ready[g], np[g] & 1);          // softmax of (g, j) done: P_g in smem, S_g free
-            if (!v_ready) {
-              mbar_wait(&v_full[stage], phase);
-              v_ready = true;
-            }
-            tc_fence_after();
-            issue_pv(g, stage, np[g] == 0);
-            ++np[g];
-          }
-          if (j + 1 >= jb[g] && j + 1 < je[g]) {        // next scores of this q tile
-            if (!k_next_ready) {
-              mbar_wait(&k_full[nstage], nphase);
-              k_next_ready = true;
-            }
-            tc_fence_after();
-            issue_s(g, nstage);
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sQ + g * Cfg::Q_BYTES + hb * (ATT_BM * 128), &tmap_q, bar_q, h * HD + hb * 64,
+                        b * p.S + q0g[g], kEvictFirst);
+        const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = j_lo; j < j_hi; ++j) {
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_expect_tx(&k_full[stage], Cfg::KV_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sK + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[stage], hb * 64,
+                        kv_row0 + j * BNKV, kEvictLast);
+          mbar_expect_tx(&v_full[stage], Cfg::KV_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sV + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_v, &v_full[stage], hb * 64,
+                        kv_row0 + j * BNKV, kEvictLast);
+          if (++stage == ST) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        umma_commit(&kv_empty[stage]);                  // every MMA reading K_j / V_j has been issued
-        stage = nstage;
-        phase = nphase;
+      }
+    } else if (warp == 9) {
+      // ------------------------------ MMA issuer ------------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // P (K-major) x V (MN-major)
+        auto issue_s = [&](int g, int stage) {    // S_g = Q_g . K^T
+          const uint32_t q_addr = smem_u32(sQ + g * Cfg::Q_BYTES);
+          const uint32_t k_addr = smem_u32(sK + stage * Cfg::KV_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + g * BNKV, umma_smem_desc(q_addr + hb * (ATT_BM * 128) + k * 32, 16, 1024),
+                           umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024), idesc_s, (hb | k) != 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+        };
+        auto issue_pv = [&](int g, int stage, bool first) {   // O_g (+)= P_g . V
+          const uint32_t p_addr = smem_u32(sP + g * Cfg::P_BYTES);
+          const uint32_t v_addr = smem_u32(sV + stage * Cfg::KV_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BNKV / 16; ++kk)
+            umma_bf16_ss(tmem_base + 2 * BNKV + g * HD,
+                         umma_smem_desc(p_addr + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
+                         umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (!first || kk != 0) ? 1u : 0u);
+          umma_commit(&o_done[g]);
+        };
+        mbar_wait(bar_q, 0);
+        int stage = 0;                       // ring slot of kv tile j
+        uint32_t phase = 0;
+        uint32_t nt[2] = {0, 0};             // kv tiles already handled per q tile (parity of s_free / p_ready)
+        if (j_lo < j_hi) {
+          mbar_wait(&k_full[0], 0);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            if (j_lo >= jb[g] && j_lo < je[g]) issue_s(g, 0);
+        }
+        for (int j = j_lo; j < j_hi; ++j) {
+          const int nstage = (stage + 1 == ST) ? 0 : stage + 1;
+          const uint32_t nphase = (stage + 1 == ST) ? (phase ^ 1) : phase;
+          bool k_next_ready = false;
+          // (1) next scores, as soon as the current ones have been copied to registers
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const bool cur = j >= jb[g] && j < je[g], nxt = j + 1 >= jb[g] && j + 1 < je[g];
+            if (nxt) {
+              if (cur) mbar_wait(&s_free[g], nt[g] & 1);
+              if (!k_next_ready) {
+                mbar_wait(&k_full[nstage], nphase);
+                k_next_ready = true;
+              }
+              tc_fence_after();
+              issue_s(g, nstage);
+            }
+          }
+          // (2) P.V of this kv tile
+          bool v_ready = false;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (j >= jb[g] && j < je[g]) {
+              mbar_wait(&p_ready[g], nt[g] & 1);
+              if (!v_ready) {
+                mbar_wait(&v_full[stage], phase);
+                v_ready = true;
+              }
+              tc_fence_after();
+              issue_pv(g, stage, nt[g] == 0);
+              ++nt[g];
+            }
+          }
+          umma_commit(&kv_empty[stage]);                  // every MMA reading K_j / V_j has been issued
+          stage = nstage;
+          phase = nphase;
+        }
       }
     }
   } else {
     // ------------------------------ softmax / correction / epilogue (8 warps, 2 q tiles) ------------------------------
+    setmaxnreg_inc<232>();
     const int g = warp >> 2;                         // q tile of this warp
     const int r = (warp & 3) * 32 + lane;            // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -632,7 +647,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       mbar_wait(&s_full[g], it & 1);
       tc_fence_after();
       att_softmax_tile<SCH, OCH>(tS_row, tO_row, sPg, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l, it > 0,
-                                 &o_done[g], (it - 1) & 1);
+                                 &o_done[g], (it - 1) & 1, &s_free[g]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[g]);
