@@ -110,14 +110,104 @@ def cpu_reference_sample(cfg, sample_tokens, steps, warmup):
     return sample_tokens / dt, dt
 
 
+def bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload):
+    """BASELINE.json config #5: autoregressive decode with the KV cache, B sequences per GPU (replicas only across
+    GPUs), greedy feedback on the device, whole step replayed as a CUDA graph.  A "step" = one rollout of
+    `new_tokens` one-token forwards for the batch; the prompt prefill is outside the timed region."""
+    import torch
+    import llm_np_cp_b200 as M
+    from llm_np_cp_b200.model import LOGITS_LAST
+    from llm_np_cp_b200 import dp
+    B, P, NT, V = a.batch, a.prompt, a.new_tokens, cfg.vocab_size
+    rng = np.random.default_rng(99 + rank)
+    prompt = torch.from_numpy(rng.integers(0, V, (B, P)).astype(np.int64)).to(dev)
+    cache = M.KVCache(max_batch=B, max_tokens=P + NT)
+    model.set_decode_graph(True)
+    tok = torch.empty((B, 1), dtype=torch.int64, device=dev)
+    tok_host = torch.empty((B, 1), dtype=torch.int64).pin_memory()
+    lg = torch.empty((B, V), dtype=torch.float32, device=dev)
+
+    def rollout(host_loop):
+        cache.reset()
+        _, l0, _, _, _ = model(prompt, use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=LOGITS_LAST)
+        tok.copy_(l0.argmax(-1, keepdim=True))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(NT):
+            if host_loop:      # e2e: the sampled ids go to the host and come back every token, like generate()
+                tok_host.copy_(tok, non_blocking=False)
+                tok.copy_(tok_host, non_blocking=True)
+            model(tok, use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=LOGITS_LAST, logits_out=lg)
+            tok.copy_(lg.argmax(-1, keepdim=True))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        rollout(False)
+    barrier()
+    model.reset_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = 0.0
+    for _ in range(a.steps):
+        ms += rollout(False)[0]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = model.stats()["launches"]
+    e2e_ms = 0.0
+    for _ in range(a.steps):
+        e2e_ms += rollout(True)[1]
+    ms, e2e_ms = dp.max_over_ranks([ms, e2e_ms], device=dev)
+    toks = B * NT * world * a.steps
+    if rank == 0:
+        L, H, I = cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size
+        q, kv = cfg.num_attention_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim
+        p_mm = L * (H * q + 2 * H * kv + q * H + 3 * H * I) + V * H
+        t_avg = P + NT / 2.0
+        bytes_step = 2.0 * p_mm + B * t_avg * L * 2 * kv * 2            # bf16 weights once + KV read (SURVEY 8d)
+        step_s = ms / 1e3 / (a.steps * NT)
+        gbs = bytes_step / step_s / 1e9
+        print(json.dumps({
+            "metric": "decode_tokens_per_sec", "value": toks / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "batch_per_gpu": B, "prompt": P, "new_tokens": NT,
+                       "parallelism": f"replicas x{world} (no collective)", "sampling": "greedy argmax on device",
+                       "cuda_graph": True, "l2": "2.47 GB of weights streamed per token step >> 126 MB L2"},
+            "ms_per_token_step": step_s * 1e3,
+            "roofline": {"bound": "hbm", "kernel": "gemm_bf16_kernel (weight streaming, M=batch)", "achieved": gbs,
+                         "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                         "bytes_per_token_step": bytes_step, "peak_source": pk["src"] + " hbm_gbs"},
+            "e2e": {"value": toks / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": B * 8 * NT * world,
+                    "d2h_bytes_per_step": B * 8 * NT * world,
+                    "what": "per token: sampled ids D2H, ids H2D, one-token forward through model(), greedy pick"},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="prefill", choices=["prefill", "decode"])
     ap.add_argument("--model", default="1b", choices=["1b", "3b", "tiny"])
-    ap.add_argument("--batch", type=int, default=8, help="sequences per GPU per step")
+    ap.add_argument("--prompt", type=int, default=16, help="decode: prompt length")
+    ap.add_argument("--new-tokens", type=int, default=128, help="decode: generated tokens per sequence")
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (default 8 prefill / 64 decode)")
     ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--cpu-sample-tokens", type=int, default=int(os.environ.get("B2_CPU_SAMPLE_TOKENS", 16)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -125,10 +215,13 @@ def main():
 
     from oracle import np_oracle as O
     cfg = O.llama_config(a.model)
+    if a.batch <= 0:
+        a.batch = 8 if a.workload == "prefill" else 64
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = f"llama-3.2-{a.model} prefill seq={a.seq}"
+    workload = (f"llama-3.2-{a.model} prefill seq={a.seq}" if a.workload == "prefill" else
+                f"llama-3.2-{a.model} decode batch={a.batch} prompt={a.prompt} new={a.new_tokens}")
     pk = peaks()
     f_tok = O.flops_per_token(cfg, a.seq)
 
@@ -163,8 +256,10 @@ def main():
 
     B, S, V = a.batch, a.seq, cfg.vocab_size
     w = synth_weights_fast(cfg, seed=0, device=dev)
-    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, 16))
+    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16))
     del w
+    if a.workload == "decode":
+        return bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload)
     rng = np.random.default_rng(1234 + rank)
     ids_host = torch.from_numpy(rng.integers(0, V, (B, S)).astype(np.int64)).pin_memory()
     ids_dev = ids_host.to(dev)
@@ -191,6 +286,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        step_resident()        # one extra untimed step so nvidia-smi is sampling under load before t0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

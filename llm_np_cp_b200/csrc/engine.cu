@@ -356,6 +356,7 @@ struct b2_engine {
   Stats st;
   bool decode_graph = false;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int64_t> graph_kernels;   // kernel nodes per captured graph (for the launch counter)
   bool capturing = false;
 };
 
@@ -891,6 +892,7 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
       // the legacy default stream cannot be captured: record on the engine's own stream, replay on `st`
       cudaStream_t cs = e->stream;
       cudaGraph_t g;
+      const int64_t launches_before = e->st.launches;
       e->capturing = true;
       CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
       int r = run_layers(e, kc, cs, ids, B, S, logits_mode, logits, nullptr);
@@ -901,10 +903,12 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
       cudaGraphExec_t ge;
       CK(cudaGraphInstantiate(&ge, g, 0));
       cudaGraphDestroy(g);
+      e->graph_kernels[key] = e->st.launches - launches_before;
+      e->st.launches = launches_before;
       it = e->graphs.emplace(key, ge).first;
     }
     CK(cudaGraphLaunch(it->second, st));
-    e->st.launches += 1;
+    e->st.launches += e->graph_kernels[key];
   } else {
     CKR(run_layers(e, kc, st, ids, B, S, logits_mode, logits, hidden));
   }

@@ -174,7 +174,7 @@ class _CausalLM:
     # ---- the reference's __call__ (llama3.2_model_numpy.py:777-830 / gemma2_model.py:830-886)
     def __call__(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, labels=None,
                  use_cache=None, output_attentions=True, output_hidden_states=True, return_dict=True, kv_cache=None,
-                 logits_mode: int = LOGITS_ALL):
+                 logits_mode: int = LOGITS_ALL, logits_out=None):
         if input_ids is not None and inputs_embeds is not None:
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         if input_ids is None:
@@ -199,10 +199,14 @@ class _CausalLM:
             cache_h = kv_cache._bind(self, B)
         H, V, Lc = self._cfg.hidden_size, self._cfg.vocab_size, self._cfg.num_hidden_layers
         logits = hidden = None
-        if logits_mode == LOGITS_ALL:
-            logits = torch.empty((B, S, V), dtype=torch.float32, device=self.device)
-        elif logits_mode == LOGITS_LAST:
-            logits = torch.empty((B, V), dtype=torch.float32, device=self.device)
+        if logits_mode != LOGITS_NONE:
+            shape = (B, S, V) if logits_mode == LOGITS_ALL else (B, V)
+            if logits_out is not None:           # caller-owned buffer (stable pointer: lets decode steps replay one CUDA graph)
+                if tuple(logits_out.shape) != shape or logits_out.dtype != torch.float32 or not logits_out.is_contiguous():
+                    raise ValueError(f"logits_out must be a contiguous float32 tensor of shape {shape}")
+                logits = logits_out
+            else:
+                logits = torch.empty(shape, dtype=torch.float32, device=self.device)
         if output_hidden_states:
             hidden = torch.empty((Lc + 1, B, S, H), dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
