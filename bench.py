@@ -204,7 +204,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="prefill", choices=["prefill", "decode"])
-    ap.add_argument("--model", default="1b", choices=["1b", "3b", "tiny"])
+    ap.add_argument("--model", default="1b", choices=["1b", "3b", "tiny", "gemma2-2b"])
+    ap.add_argument("--hf-flags", action="store_true", help="gemma2: attention soft-cap + sliding window (HF semantics)")
     ap.add_argument("--prompt", type=int, default=16, help="decode: prompt length")
     ap.add_argument("--new-tokens", type=int, default=128, help="decode: generated tokens per sequence")
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (default 8 prefill / 64 decode)")
@@ -214,14 +215,15 @@ def main():
     a = ap.parse_args()
 
     from oracle import np_oracle as O
-    cfg = O.llama_config(a.model)
+    cfg = O.gemma2_config("2b") if a.model == "gemma2-2b" else O.llama_config(a.model)
     if a.batch <= 0:
         a.batch = 8 if a.workload == "prefill" else 64
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = (f"llama-3.2-{a.model} prefill seq={a.seq}" if a.workload == "prefill" else
-                f"llama-3.2-{a.model} decode batch={a.batch} prompt={a.prompt} new={a.new_tokens}")
+    fam = "gemma-2-2b" if a.model == "gemma2-2b" else f"llama-3.2-{a.model}"
+    workload = (f"{fam} prefill seq={a.seq}" + (" hf-flags" if a.hf_flags else "") if a.workload == "prefill" else
+                f"{fam} decode batch={a.batch} prompt={a.prompt} new={a.new_tokens}")
     pk = peaks()
     f_tok = O.flops_per_token(cfg, a.seq)
 
@@ -256,7 +258,10 @@ def main():
 
     B, S, V = a.batch, a.seq, cfg.vocab_size
     w = synth_weights_fast(cfg, seed=0, device=dev)
-    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16))
+    if cfg.family == "gemma2":
+        model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16), hf_flags=a.hf_flags)
+    else:
+        model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16))
     del w
     if a.workload == "decode":
         return bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload)
@@ -329,7 +334,7 @@ def main():
             "metric": "prefill_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "model": f"Llama-3.2-{a.model.upper()} shapes, random-init bf16 weights (std 0.02)",
+            "config": {"workload": workload, "model": f"{fam} shapes, random-init bf16 weights (std 0.02)",
                        "global_batch": B * world, "seq_len": S, "tokens_per_step_per_gpu": B * S,
                        "parallelism": f"dp{world} (batch-sharded, weights replicated, no collective)",
                        "logits": "full [B,S,V] fp32 written to HBM every step",
