@@ -292,6 +292,7 @@ def main():
     if rank == 0:
         sampler.start()
         step_resident()        # one extra untimed step so nvidia-smi is sampling under load before t0
+    model.reset_stats()        # only the timed steps below count towards the roofline figures
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

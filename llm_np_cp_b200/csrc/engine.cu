@@ -166,7 +166,7 @@ static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
   if (epi == EPI_GLU && p.N % 64 != 0) return fail(B2_ERR_ARG, "GLU GEMM N=%d must be a multiple of 64", p.N);
   if (p.split_k < 1 || (p.K / GEMM_BK) % p.split_k != 0)
     return fail(B2_ERR_ARG, "split_k=%d must divide K/64=%d", p.split_k, p.K / GEMM_BK);
-  if (p.split_k > 1 && epi != EPI_RESID) return fail(B2_ERR_ARG, "split_k needs the residual epilogue");
+  if (p.split_k > 1 && epi != EPI_RESID && epi != EPI_F32) return fail(B2_ERR_ARG, "split_k needs the residual or fp32 epilogue");
   if ((epi == EPI_F32 || epi == EPI_RESID) && p.ldo % 4 != 0) return fail(B2_ERR_ARG, "fp32 output stride %d must be a multiple of 4", p.ldo);
 #define GEMM_CASE(BN_, EPI_) \
   if (bn == BN_ && epi == EPI_) return launch_gemm_t<BN_, EPI_>(ta, tb, tc, p, st)
@@ -311,6 +311,8 @@ static float f16_to_f32(uint16_t h) {
 // ------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------
+constexpr int MAX_SPLIT = 8;
+
 struct Layer {
   bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wd = nullptr;
   float *g_in = nullptr, *g_post_attn = nullptr, *g_pre_ffn = nullptr, *g_post_ffn = nullptr;
@@ -346,7 +348,7 @@ struct b2_engine {
   float *rope_cos = nullptr, *rope_sin = nullptr;
   // workspace
   int ws_tokens = 0, ws_batch = 0;
-  float *x = nullptr, *y = nullptr, *xl = nullptr;
+  float *x = nullptr, *y = nullptr, *xl = nullptr, *part = nullptr;   // part: [MAX_SPLIT][128][H] split-K partials (skinny GEMMs)
   bf16 *xn = nullptr, *q = nullptr, *att = nullptr, *hb = nullptr, *xnl = nullptr;
   int64_t* ids_ws = nullptr;
   float* logits_ws = nullptr;
@@ -404,13 +406,13 @@ static int pick_band(int N, int K) {
 
 // C = A . W^T through the engine (cached descriptors, stats)
 static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* a, int lda, const bf16* w, GemmParams p,
-                    int a_rows = 0) {
+                    int a_rows = 0, int c_rows = 0) {
   const CUtensorMap *ta, *tb, *tc;
   if (!a_rows) a_rows = e->ws_tokens > p.M ? e->ws_tokens : p.M;
   CKR(get_tmap(e, a, a_rows, p.K, lda, GEMM_BM, &ta));
   CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, bn, &tb));
   tc = ta;
-  if (epi == EPI_F32 || epi == EPI_RESID) CKR(get_tmap(e, p.out, p.M, p.N, p.ldo, 32, &tc, true));
+  if (epi == EPI_F32 || epi == EPI_RESID) CKR(get_tmap(e, p.out, c_rows ? c_rows : p.M, p.N, p.ldo, 32, &tc, true));
   p.band_m = pick_band(p.N, p.k_wrap);
   time_begin(e, st, 2.0 * p.M * static_cast<double>(p.N) * p.K, 0);
   int r = launch_gemm(bn, epi, *ta, *tb, *tc, p, st);
@@ -474,9 +476,9 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
 }
 
 static void free_ws(b2_engine* e) {
-  cudaFree(e->x); cudaFree(e->y); cudaFree(e->xl); cudaFree(e->xn); cudaFree(e->q); cudaFree(e->att);
+  cudaFree(e->x); cudaFree(e->y); cudaFree(e->xl); cudaFree(e->part); cudaFree(e->xn); cudaFree(e->q); cudaFree(e->att);
   cudaFree(e->hb); cudaFree(e->xnl); cudaFree(e->ids_ws);
-  e->x = e->y = e->xl = nullptr;
+  e->x = e->y = e->xl = e->part = nullptr;
   e->xn = e->q = e->att = e->hb = e->xnl = nullptr;
   e->ids_ws = nullptr;
   e->tmaps.clear();
@@ -697,14 +699,17 @@ static int ensure_ws(b2_engine* e, int M, int B) {
   CK(cudaMalloc(&e->hb, Mp * I * 2));
   CK(cudaMalloc(&e->ids_ws, Mp * 8));
   CK(cudaMalloc(&e->xl, Bp * H * 4));
+  CK(cudaMalloc(&e->part, static_cast<size_t>(MAX_SPLIT) * 128 * H * 4));
   CK(cudaMalloc(&e->xnl, Bp * H * 2));
   e->ws_tokens = static_cast<int>(Mp);
   e->ws_batch = static_cast<int>(Bp);
   return B2_OK;
 }
 
-static int rmsnorm(b2_engine* e, cudaStream_t st, const float* x, const float* g, bf16* ob, float* of, int M) {
-  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, ob, e->cfg.hidden_size, 0, of, M, e->cfg.hidden_size, e->cfg.rms_norm_eps);
+// nsplit > 0: first fold the pending split-K partials of the previous o_proj / down_proj into x
+static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16* ob, float* of, int M, int nsplit = 0) {
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, ob, e->cfg.hidden_size, 0, of, M, e->cfg.hidden_size, e->cfg.rms_norm_eps,
+                                              e->part, nsplit, static_cast<size_t>(128) * e->cfg.hidden_size);
   CK(cudaGetLastError());
   e->st.launches++;
   return B2_OK;
@@ -720,6 +725,15 @@ static GemmParams base_params(int M, int N, int K) {
   p.band_m = 32;
   p.split_k = 1;
   return p;
+}
+
+// split-K factor for a skinny GEMM (M <= 128): aim at >= ~128 CTAs with >= 8 k-blocks each
+static int pick_split(int N, int K, int bn) {
+  const int tiles = (N + bn - 1) / bn, kb = K / GEMM_BK;
+  int best = 1;
+  for (int sp = 2; sp <= MAX_SPLIT; sp *= 2)
+    if (kb % sp == 0 && kb / sp >= 8 && tiles * sp <= 304) best = sp;
+  return best;
 }
 
 // tile width for a GEMM with M rows: wide tiles for prefill, narrow ones so skinny decode GEMMs spread over SMs
@@ -738,6 +752,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
   const b2_config& c = e->cfg;
   const int M = B * S, H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, HD = c.head_dim;
   const bool decode = (S == 1);
+  const bool skinny = M <= 128 && !hidden;     // few rows: split-K so the weight stream covers all SMs
+  int pend = 0;                                // split-K partials of the last down_proj not yet folded into x
   const float escale = c.gemma ? sqrtf(static_cast<float>(H)) : 1.0f;
   embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(ids), e->embed, e->x, M, H, c.vocab_size, escale);
   CK(cudaGetLastError());
@@ -747,7 +763,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
   for (int li = 0; li < L; ++li) {
     Layer& Ly = e->layers[li];
     if (hidden) CK(cudaMemcpyAsync(hidden + static_cast<size_t>(li) * M * H, e->x, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
-    CKR(rmsnorm(e, st, e->x, Ly.g_in, e->xn, nullptr, M));
+    CKR(rmsnorm(e, st, e->x, Ly.g_in, e->xn, nullptr, M, pend));
+    pend = 0;
     {  // fused QKV projection + RoPE + KV-cache append
       GemmParams p = base_params(M, e->qkv_n, H);
       p.q_cols = e->q_cols;
@@ -787,14 +804,30 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     }
     if (!c.gemma) {
       GemmParams p = base_params(M, H, e->q_cols);
-      p.out = e->x; p.ldo = H;
-      CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->att, e->q_cols, Ly.wo, p));   // x += attn . Wo^T
-      CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M));
+      int ns = 0;
+      if (skinny) {   // split-K partials, summed in fixed order by the norm that follows (deterministic)
+        p.out = e->part; p.ldo = H; p.split_rows = 128;
+        p.split_k = ns = pick_split(H, e->q_cols, 64);
+        CKR(eng_gemm(e, st, 64, EPI_F32, e->att, e->q_cols, Ly.wo, p, 0, MAX_SPLIT * 128));
+      } else {
+        p.out = e->x; p.ldo = H;
+        CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->att, e->q_cols, Ly.wo, p));   // x += attn . Wo^T
+      }
+      CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M, ns));
     } else {
       GemmParams p = base_params(M, H, e->q_cols);
-      p.out = e->y; p.ldo = H;
-      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->att, e->q_cols, Ly.wo, p));
-      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, e->y, Ly.g_post_attn, M, H, c.rms_norm_eps);
+      const float* ysrc = e->y;
+      int ns = 1;
+      if (skinny) {
+        p.out = e->part; p.ldo = H; p.split_rows = 128;
+        p.split_k = ns = pick_split(H, e->q_cols, 64);
+        ysrc = e->part;
+        CKR(eng_gemm(e, st, 64, EPI_F32, e->att, e->q_cols, Ly.wo, p, 0, MAX_SPLIT * 128));
+      } else {
+        p.out = e->y; p.ldo = H;
+        CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->att, e->q_cols, Ly.wo, p));
+      }
+      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, ysrc, Ly.g_post_attn, M, H, c.rms_norm_eps, ns, static_cast<size_t>(128) * H);
       CK(cudaGetLastError());
       e->st.launches++;
       CKR(rmsnorm(e, st, e->x, Ly.g_pre_ffn, e->xn, nullptr, M));
@@ -806,20 +839,38 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     }
     if (!c.gemma) {
       GemmParams p = base_params(M, H, I);
-      p.out = e->x; p.ldo = H;
-      CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->hb, I, Ly.wd, p));              // x += h . Wd^T
+      if (skinny) {
+        p.out = e->part; p.ldo = H; p.split_rows = 128;
+        p.split_k = pend = pick_split(H, I, 64);      // folded into x by the next layer's input norm / the final norm
+        CKR(eng_gemm(e, st, 64, EPI_F32, e->hb, I, Ly.wd, p, 0, MAX_SPLIT * 128));
+      } else {
+        p.out = e->x; p.ldo = H;
+        CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->hb, I, Ly.wd, p));            // x += h . Wd^T
+      }
     } else {
       GemmParams p = base_params(M, H, I);
-      p.out = e->y; p.ldo = H;
-      CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->hb, I, Ly.wd, p));
-      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, e->y, Ly.g_post_ffn, M, H, c.rms_norm_eps);
+      const float* ysrc = e->y;
+      int ns = 1;
+      if (skinny) {
+        p.out = e->part; p.ldo = H; p.split_rows = 128;
+        p.split_k = ns = pick_split(H, I, 64);
+        ysrc = e->part;
+        CKR(eng_gemm(e, st, 64, EPI_F32, e->hb, I, Ly.wd, p, 0, MAX_SPLIT * 128));
+      } else {
+        p.out = e->y; p.ldo = H;
+        CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->hb, I, Ly.wd, p));
+      }
+      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, ysrc, Ly.g_post_ffn, M, H, c.rms_norm_eps, ns, static_cast<size_t>(128) * H);
       CK(cudaGetLastError());
       e->st.launches++;
     }
   }
   // final norm + lm_head (tied to the embedding, llama3.2_model_numpy.py:1025-1026)
   float* hid_last = hidden ? hidden + static_cast<size_t>(L) * M * H : nullptr;
-  if (logits_mode == B2_LOGITS_ALL || hidden) CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, hid_last, M));
+  if (logits_mode == B2_LOGITS_ALL || hidden) {
+    CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, hid_last, M, pend));
+    pend = 0;
+  }
   if (logits_mode == B2_LOGITS_ALL) {
     GemmParams p = base_params(M, c.vocab_size, H);
     p.out = logits; p.ldo = c.vocab_size; p.softcap = c.final_logit_softcap;
@@ -828,8 +879,12 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     const bf16* a = e->xn;
     int lda_rows = 0;
     if (S == 1) {
-      if (!hidden) CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, nullptr, M));
+      if (!hidden) CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, nullptr, M, pend));
     } else {
+      if (pend) {   // fold the last down_proj partials into x before gathering rows (xn output unused here)
+        CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, nullptr, M, pend));
+        pend = 0;
+      }
       gather_last_kernel<<<B, 256, 0, st>>>(e->x, e->xl, B, S, H);
       CK(cudaGetLastError());
       e->st.launches++;
@@ -1017,14 +1072,14 @@ extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
 extern "C" int b2_op_rmsnorm(const float* x, const float* g, void* ob, float* of, int M, int H, float eps, void* stream) {
   CKR(require_gpu(0));
   if (H % 128 || H > 128 * NORM_MAXV) return fail(B2_ERR_ARG, "H=%d must be a multiple of 128 and <= %d", H, 128 * NORM_MAXV);
-  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, static_cast<bf16*>(ob), H, 0, of, M, H, eps);
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(const_cast<float*>(x), g, static_cast<bf16*>(ob), H, 0, of, M, H, eps, nullptr, 0, 0);
   CK(cudaGetLastError());
   return B2_OK;
 }
 extern "C" int b2_op_add_rmsnorm(float* x, const float* y, const float* g, int M, int H, float eps, void* stream) {
   CKR(require_gpu(0));
   if (H % 128 || H > 128 * NORM_MAXV) return fail(B2_ERR_ARG, "H=%d must be a multiple of 128 and <= %d", H, 128 * NORM_MAXV);
-  add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, g, M, H, eps);
+  add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, g, M, H, eps, 1, 0);
   CK(cudaGetLastError());
   return B2_OK;
 }

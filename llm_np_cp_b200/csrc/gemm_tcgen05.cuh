@@ -30,7 +30,9 @@ struct GemmParams {
   int M, N, K;   // K = contraction length seen by A (2*k_wrap in hi/lo "precise" mode)
   int k_wrap;    // W k-coordinate = k % k_wrap
   int band_m;    // rasterisation: m-blocks per band (operand tiles stay hot in L2 inside a band)
-  int split_k;   // >1: K is split across CTAs (skinny GEMMs); only EPI_RESID supports it (reduce-add)
+  int split_k;   // >1: K is split across CTAs (skinny GEMMs): EPI_RESID reduce-adds, EPI_F32 stores split s at rows
+                 // [s*split_rows, s*split_rows + M) of `out` (deterministic: the consumer sums the partials in order)
+  int split_rows;
   // EPI_BF16 / EPI_GLU (direct stores); EPI_F32 / EPI_RESID go through the output tensor map
   void* out;
   int ldo;         // row stride of out, in elements
@@ -93,7 +95,7 @@ __device__ __forceinline__ void split_lo(const float (&v)[32], float (&lo)[32]) 
 // warps sharing that quarter (takes column groups of its parity), `slab` = this warp's 4 KB staging.
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtensorMap* tmap_c, uint8_t* slab,
-                                              uint32_t tacc, int mb, int nb, int quarter, int half, int lane) {
+                                              uint32_t tacc, int mb, int nb, int ks, int quarter, int half, int lane) {
   const int row0 = mb * GEMM_BM + quarter * 32;
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
@@ -123,7 +125,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && row0 < p.M) {
-        if (EPI == EPI_F32) tma_store_2d(tmap_c, slab, col, row0);
+        if (EPI == EPI_F32) tma_store_2d(tmap_c, slab, col, ks * p.split_rows + row0);
         else tma_reduce_add_2d(tmap_c, slab, col, row0);   // x += acc  (fp32 residual stream)
         tma_store_commit();
       }
@@ -377,7 +379,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tile_coords(tile, mb, nb, kb0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      gemm_epilogue<BN, EPI>(p, &tmap_c, slab, tmem_base + acc * BN, mb, nb, quarter, half, lane);
+      gemm_epilogue<BN, EPI>(p, &tmap_c, slab, tmem_base + acc * BN, mb, nb, kb0 / KB, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
