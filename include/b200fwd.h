@@ -109,6 +109,9 @@ int b2_set_decode_graph(b2_engine* e, int enable);
 int b2_sample_min_p(b2_engine* e, const float* logits_dev, int B, int ld, float p_base, const float* u_dev,
                     int64_t* out_ids_dev, float* probs_dev, void* stream);
 
+/* greedy pick on the device: out_ids_dev[b] = argmax(logits_dev[b, :V]) (lowest index on ties, like np.argmax) */
+int b2_argmax(b2_engine* e, const float* logits_dev, int B, int ld, int64_t* out_ids_dev, void* stream);
+
 /* -------- instrumentation */
 typedef struct b2_stats {
   int64_t launches;        /* kernels launched by this library since the last reset */

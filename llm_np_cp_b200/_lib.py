@@ -45,6 +45,7 @@ SYMBOLS = [
     ("b2_forward_host", _I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     ("b2_set_decode_graph", _I, [_P, _I]),
     ("b2_sample_min_p", _I, [_P, _P, _I, _I, _F, _P, _P, _P, _P]),
+    ("b2_argmax", _I, [_P, _P, _I, _I, _P, _P]),
     ("b2_set_timing", _I, [_P, _I]),
     ("b2_get_stats", _I, [_P, C.POINTER(B2Stats)]),
     ("b2_reset_stats", _I, [_P]),

@@ -89,6 +89,63 @@ rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16
   }
 }
 
+// Few-row variant (decode, M <= 128): one 256-thread CTA per row so the row's loads (and the split-K partials)
+// are all in flight at once instead of serialised inside a single warp.  Same arithmetic and summation order of
+// the partials as rmsnorm_kernel.
+__global__ void __launch_bounds__(256)
+rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
+                   float* __restrict__ out_f32, int H, float eps, const float* __restrict__ partials, int nsplit,
+                   size_t split_stride) {
+  __shared__ float red[8];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int nv4 = H >> 2;                       // float4 per row (<= 768)
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H);
+  float4 v[3];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int idx = tid + i * 256;
+    if (idx < nv4) {
+      v[i] = xr[idx];
+      if (nsplit > 0) {
+        float4 pp[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < nsplit) pp[s] = reinterpret_cast<const float4*>(partials + s * split_stride + static_cast<size_t>(row) * H)[idx];
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < nsplit) {
+            v[i].x += pp[s].x;
+            v[i].y += pp[s].y;
+            v[i].z += pp[s].z;
+            v[i].w += pp[s].w;
+          }
+        xr[idx] = v[i];
+      }
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];     // same order in every thread
+  const float rs = 1.0f / sqrtf(tot / static_cast<float>(H) + eps);
+  const float4* gr = reinterpret_cast<const float4*>(g);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int idx = tid + i * 256;
+    if (idx < nv4) {
+      const float4 gg = __ldg(gr + idx);
+      const float4 o = make_float4(v[i].x * rs * gg.x, v[i].y * rs * gg.y, v[i].z * rs * gg.z, v[i].w * rs * gg.w);
+      if (out_bf16)
+        *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * H + idx * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * H)[idx] = o;
+    }
+  }
+}
+
 // Gemma-2 post-norms: x += rmsnorm(y) * g   (gemma2_model.py:633-637, :641-643)
 __global__ void __launch_bounds__(256)
 add_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g, int M, int H,
@@ -143,6 +200,62 @@ gather_last_kernel(const float* __restrict__ src, float* __restrict__ dst, int B
 
 __global__ void add_scalar_kernel(int* p, int v) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *p += v;
+}
+
+// greedy pick: out[b] = argmax_v logits[b, v] (lowest index on ties, like np.argmax); one CTA per row
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const float* __restrict__ logits, int ld, int V, long long* __restrict__ out) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float4* x4 = reinterpret_cast<const float4*>(logits + static_cast<size_t>(b) * ld);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < V / 4; i += 1024) {
+    const float4 v = x4[i];
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e[k] > best) {
+        best = e[k];
+        bi = i * 4 + k;
+      }
+  }
+  for (int i = (V / 4) * 4 + tid; i < V; i += 1024) {
+    const float v = logits[static_cast<size_t>(b) * ld + i];
+    if (v > best) {
+      best = v;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if ((tid & 31) == 0) {
+    sv[tid >> 5] = best;
+    si[tid >> 5] = bi;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    best = sv[tid];
+    bi = si[tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (tid == 0) out[b] = bi;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

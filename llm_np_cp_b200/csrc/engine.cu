@@ -708,6 +708,13 @@ static int ensure_ws(b2_engine* e, int M, int B) {
 
 // nsplit > 0: first fold the pending split-K partials of the previous o_proj / down_proj into x
 static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16* ob, float* of, int M, int nsplit = 0) {
+  if (M <= 128) {   // decode / tiny prompts: a CTA per row keeps every load of the row in flight
+    rmsnorm_row_kernel<<<M, 256, 0, st>>>(x, g, ob, of, e->cfg.hidden_size, e->cfg.rms_norm_eps, e->part, nsplit,
+                                          static_cast<size_t>(128) * e->cfg.hidden_size);
+    CK(cudaGetLastError());
+    e->st.launches++;
+    return B2_OK;
+  }
   rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, ob, e->cfg.hidden_size, 0, of, M, e->cfg.hidden_size, e->cfg.rms_norm_eps,
                                               e->part, nsplit, static_cast<size_t>(128) * e->cfg.hidden_size);
   CK(cudaGetLastError());
@@ -1016,6 +1023,15 @@ extern "C" int b2_forward_host(b2_engine* e, b2_cache* cache, const int64_t* ids
 extern "C" int b2_set_decode_graph(b2_engine* e, int enable) {
   if (!e) return fail(B2_ERR_ARG, "null engine");
   e->decode_graph = enable != 0;
+  return B2_OK;
+}
+
+extern "C" int b2_argmax(b2_engine* e, const float* logits, int B, int ld, int64_t* out_ids, void* stream) {
+  if (!e || !logits || !out_ids || B <= 0) return fail(B2_ERR_ARG, "bad argmax arguments");
+  CK(cudaSetDevice(e->device));
+  argmax_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, e->cfg.vocab_size, reinterpret_cast<long long*>(out_ids));
+  CK(cudaGetLastError());
+  e->st.launches++;
   return B2_OK;
 }
 

@@ -217,6 +217,16 @@ class _CausalLM:
         hs = tuple(hidden[i] for i in range(Lc + 1)) if hidden is not None else None
         return (None, logits, kv_cache, hs, None)
 
+    def argmax(self, logits, out=None):
+        """Greedy pick on the device: [B,V] fp32 logits -> [B] int64 (np.argmax semantics)."""
+        lg = logits if logits.dim() == 2 else logits.reshape(-1, logits.shape[-1])
+        B, V = lg.shape
+        if out is None:
+            out = torch.empty(B, dtype=torch.int64, device=self.device)
+        check(_lib.lib().b2_argmax(self._h, lg.data_ptr(), B, lg.stride(0), out.data_ptr(),
+                                   torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
     # ---- instrumentation
     def set_timing(self, on: bool):
         check(_lib.lib().b2_set_timing(self._h, 1 if on else 0))

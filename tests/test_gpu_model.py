@@ -149,6 +149,11 @@ def test_forward_host_and_sampling():
     assert np.abs(probs.cpu().numpy() - want).max() < 1e-5
     for b in range(lg.shape[0]):
         assert want[b, int(tok[b])] > 0
+    # greedy pick == np.argmax (lowest index on ties)
+    lgd = lg.to("cuda")
+    lgd[1, 7] = lgd[1].max() + 1.0
+    lgd[1, 300] = lgd[1, 7]
+    assert model.argmax(lgd).cpu().tolist() == lgd.cpu().numpy().argmax(-1).tolist()
     # inverse-CDF property: frequencies follow the distribution
     cnt = np.zeros(cfg.vocab_size)
     g = torch.Generator().manual_seed(1)
