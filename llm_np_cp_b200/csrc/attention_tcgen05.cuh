@@ -241,16 +241,6 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / (p.NH / p.NKV);
   const int q0 = qt * ATT_BM;
-  const int t0 = *p.t0_ptr;
-  const int T = t0 + p.S;                                   // kv length after this call's append
-  // kv range this q tile can see
-  int kv_end = T;
-  if (p.causal) kv_end = min(T, t0 + q0 + ATT_BM);
-  int kv_begin = 0;
-  if (p.window > 0) kv_begin = max(0, t0 + q0 - p.window + 1);
-  const int jt0 = kv_begin / BNKV;
-  const int jt1 = (kv_end + BNKV - 1) / BNKV;               // tiles [jt0, jt1)
-  const int n_tiles = jt1 - jt0;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -268,10 +258,22 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                               // Q/K/V and the cache length come from the preceding kernels
+  const int t0 = *p.t0_ptr;
+  const int T = t0 + p.S;                                   // kv length after this call's append
+  // kv range this q tile can see
+  int kv_end = T;
+  if (p.causal) kv_end = min(T, t0 + q0 + ATT_BM);
+  int kv_begin = 0;
+  if (p.window > 0) kv_begin = max(0, t0 + q0 - p.window + 1);
+  const int jt0 = kv_begin / BNKV;
+  const int jt1 = (kv_end + BNKV - 1) / BNKV;               // tiles [jt0, jt1)
+  const int n_tiles = jt1 - jt0;
   const uint32_t tS = tmem_base;            // S accumulator columns [0, BNKV)
   const uint32_t tO = tmem_base + BNKV;     // O accumulator columns [BNKV, BNKV + HD)
 
@@ -461,26 +463,6 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int pi = n_pairs - 1 - static_cast<int>(blockIdx.x);    // heaviest pairs first
   const int h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / (p.NH / p.NKV);
-  const int t0 = *p.t0_ptr;
-  const int T = t0 + p.S;
-  // per q tile g: rows [q0g, q0g+128), kv tiles [jb[g], je[g])
-  int q0g[2], jb[2], je[2];
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    q0g[g] = (2 * pi + g) * ATT_BM;
-    if (2 * pi + g >= n_qt) {
-      jb[g] = je[g] = 0;          // tile does not exist (odd tile count)
-    } else {
-      int kv_end = T;
-      if (p.causal) kv_end = min(T, t0 + q0g[g] + ATT_BM);
-      int kv_begin = 0;
-      if (p.window > 0) kv_begin = max(0, t0 + q0g[g] - p.window + 1);
-      jb[g] = kv_begin / BNKV;
-      je[g] = (kv_end + BNKV - 1) / BNKV;
-    }
-  }
-  const int j_lo = (je[1] > jb[1]) ? min(jb[0], jb[1]) : jb[0];
-  const int j_hi = max(je[0], je[1]);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -501,10 +483,32 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                               // Q/K/V and the cache length come from the preceding kernels
+  const int t0 = *p.t0_ptr;
+  const int T = t0 + p.S;
+  // per q tile g: rows [q0g, q0g+128), kv tiles [jb[g], je[g])
+  int q0g[2], jb[2], je[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    q0g[g] = (2 * pi + g) * ATT_BM;
+    if (2 * pi + g >= n_qt) {
+      jb[g] = je[g] = 0;          // tile does not exist (odd tile count)
+    } else {
+      int kv_end = T;
+      if (p.causal) kv_end = min(T, t0 + q0g[g] + ATT_BM);
+      int kv_begin = 0;
+      if (p.window > 0) kv_begin = max(0, t0 + q0g[g] - p.window + 1);
+      jb[g] = kv_begin / BNKV;
+      je[g] = (kv_end + BNKV - 1) / BNKV;
+    }
+  }
+  const int j_lo = (je[1] > jb[1]) ? min(jb[0], jb[1]) : jb[0];
+  const int j_hi = max(je[0], je[1]);
 
   if (warp >= 8) {
     setmaxnreg_dec<40>();
@@ -681,6 +685,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
                    int NKV, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap, int window) {
   constexpr int LPP = HD / 64;                   // lanes per kv position
   constexpr int PPI = 32 / LPP;                  // positions per warp iteration
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 4 + warp;          // (b, h)
   if (gw >= B * NH) return;

@@ -31,6 +31,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start (CTA scheduling, barrier init, TMEM alloc, descriptor prefetch) while its predecessor is still
+// draining.  pdl_trigger() lets the NEXT kernel start early; pdl_wait() blocks until the PREVIOUS kernel has
+// completed and its memory is visible -- it must precede every access to data the predecessor produced.
+// Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // register budget hand-over between warpgroups (all 4 warps of a warpgroup must execute it)
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }

@@ -10,6 +10,8 @@ namespace b2 {
 __global__ void __launch_bounds__(256)
 embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ table, float* __restrict__ x,
              int M, int H, int V, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= M) return;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
                int ld_out, int lo_off, float* __restrict__ out_f32, int M, int H, float eps,
                const float* __restrict__ partials, int nsplit, size_t split_stride) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= M) return;
@@ -96,6 +100,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
                    float* __restrict__ out_f32, int H, float eps, const float* __restrict__ partials, int nsplit,
                    size_t split_stride) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   const int row = blockIdx.x, tid = threadIdx.x;
   const int nv4 = H >> 2;                       // float4 per row (<= 768)
@@ -149,7 +155,9 @@ rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bflo
 // Gemma-2 post-norms: x += rmsnorm(y) * g   (gemma2_model.py:633-637, :641-643)
 __global__ void __launch_bounds__(256)
 add_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g, int M, int H,
-                   float eps, int nsplit, size_t split_stride) {   // nsplit > 1: y = sum of split-K partials
+                   float eps, int nsplit, size_t split_stride) {
+  pdl_trigger();
+  pdl_wait();   // nsplit > 1: y = sum of split-K partials
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= M) return;
@@ -192,6 +200,8 @@ add_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ y, const flo
 // dst[b, :] = src[b*S + S-1, :]  (last position of every sequence; feeds last-token-only logits)
 __global__ void __launch_bounds__(256)
 gather_last_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int S, int H) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const float4* s = reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * S + S - 1) * H);
   float4* d = reinterpret_cast<float4*>(dst + static_cast<size_t>(b) * H);
@@ -199,12 +209,16 @@ gather_last_kernel(const float* __restrict__ src, float* __restrict__ dst, int B
 }
 
 __global__ void add_scalar_kernel(int* p, int v) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) *p += v;
 }
 
 // greedy pick: out[b] = argmax_v logits[b, v] (lowest index on ties, like np.argmax); one CTA per row
 __global__ void __launch_bounds__(1024)
 argmax_kernel(const float* __restrict__ logits, int ld, int V, long long* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sv[32];
   __shared__ int si[32];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -283,6 +297,8 @@ __device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
 __global__ void __launch_bounds__(1024)
 min_p_sample_kernel(const float* __restrict__ logits, int ld, int V, float p_base, const float* __restrict__ u,
                     long long* __restrict__ out_ids, float* __restrict__ probs_out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[33];
   __shared__ float seg[1024];
   __shared__ int pick_seg;

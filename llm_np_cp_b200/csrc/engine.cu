@@ -128,6 +128,28 @@ struct Stats {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
 };
 
+// Every kernel goes through this: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (PDL),
+// so a kernel's launch + prologue overlap its predecessor's tail (B2_NO_PDL=1 turns it off).
+static bool pdl_enabled() {
+  static const bool on = getenv("B2_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static int g_num_sms[16] = {0};
 static int num_sms() {
   int dev = 0;
@@ -153,8 +175,7 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM, n_blocks = (p.N + BN - 1) / BN;
   const int total = m_blocks * n_blocks * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, tc, p);
-  CK(cudaGetLastError());
+  CK(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN>::SMEM_BYTES, st, ta, tb, tc, p));
   return B2_OK;
 }
 
@@ -203,8 +224,7 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     if (dev < 16) attr[dev] = true;
   }
   dim3 grid((p.S + ATT_BM - 1) / ATT_BM, p.NH, p.B);
-  kern<<<grid, ATT_THREADS, AttnCfg<HD>::SMEM_BYTES, st>>>(tq, tk, tv, p);
-  CK(cudaGetLastError());
+  CK(launch_k(kern, grid, dim3(ATT_THREADS), AttnCfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
   return B2_OK;
 }
 
@@ -221,8 +241,7 @@ static int launch_attn_pair_t(const CUtensorMap& tq, const CUtensorMap& tk, cons
   }
   const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
   dim3 grid((n_qt + 1) / 2, p.NH, p.B);
-  kern<<<grid, ATT2_THREADS, Attn2Cfg<HD>::SMEM_BYTES, st>>>(tq, tk, tv, p);
-  CK(cudaGetLastError());
+  CK(launch_k(kern, grid, dim3(ATT2_THREADS), Attn2Cfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
   return B2_OK;
 }
 
@@ -254,9 +273,8 @@ static int attn_decode(const bf16* q, int ldq, const bf16* kc, const bf16* vc, b
   const int grid = (B * NH + 3) / 4;
 #define DEC(HD_)                                                                                              \
   if (HD == HD_) {                                                                                            \
-    attn_decode_kernel<HD_><<<grid, 128, 0, st>>>(q, ldq, kc, vc, out, ldo, B, NH, NKV, Tmax, t0_ptr, scale, \
-                                                  softcap, window);                                           \
-    CK(cudaGetLastError());                                                                                   \
+    CK(launch_k(attn_decode_kernel<HD_>, dim3(grid), dim3(128), 0, st, q, ldq, kc, vc, out, ldo, B, NH, NKV, Tmax, t0_ptr, \
+                scale, softcap, window));                                                                     \
     return B2_OK;                                                                                             \
   }
   DEC(64) DEC(128) DEC(256)
@@ -709,15 +727,13 @@ static int ensure_ws(b2_engine* e, int M, int B) {
 // nsplit > 0: first fold the pending split-K partials of the previous o_proj / down_proj into x
 static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16* ob, float* of, int M, int nsplit = 0) {
   if (M <= 128) {   // decode / tiny prompts: a CTA per row keeps every load of the row in flight
-    rmsnorm_row_kernel<<<M, 256, 0, st>>>(x, g, ob, of, e->cfg.hidden_size, e->cfg.rms_norm_eps, e->part, nsplit,
-                                          static_cast<size_t>(128) * e->cfg.hidden_size);
-    CK(cudaGetLastError());
+    CK(launch_k(rmsnorm_row_kernel, dim3(M), dim3(256), 0, st, x, g, ob, of, e->cfg.hidden_size, e->cfg.rms_norm_eps,
+                static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * e->cfg.hidden_size));
     e->st.launches++;
     return B2_OK;
   }
-  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, ob, e->cfg.hidden_size, 0, of, M, e->cfg.hidden_size, e->cfg.rms_norm_eps,
-                                              e->part, nsplit, static_cast<size_t>(128) * e->cfg.hidden_size);
-  CK(cudaGetLastError());
+  CK(launch_k(rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, g, ob, e->cfg.hidden_size, 0, of, M, e->cfg.hidden_size,
+              e->cfg.rms_norm_eps, static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * e->cfg.hidden_size));
   e->st.launches++;
   return B2_OK;
 }
@@ -762,8 +778,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
   const bool skinny = M <= 128 && !hidden;     // few rows: split-K so the weight stream covers all SMs
   int pend = 0;                                // split-K partials of the last down_proj not yet folded into x
   const float escale = c.gemma ? sqrtf(static_cast<float>(H)) : 1.0f;
-  embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(ids), e->embed, e->x, M, H, c.vocab_size, escale);
-  CK(cudaGetLastError());
+  CK(launch_k(embed_kernel, dim3((M + 7) / 8), dim3(256), 0, st, reinterpret_cast<const long long*>(ids),
+              static_cast<const bf16*>(e->embed), e->x, M, H, c.vocab_size, escale));
   e->st.launches++;
   const int causal = (c.always_causal || S > 2) ? 1 : 0;   // llama3.2_model_numpy.py:479
   const float scale = c.attn_scale > 0.f ? c.attn_scale : 1.0f / sqrtf(static_cast<float>(HD));
@@ -834,8 +850,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
         p.out = e->y; p.ldo = H;
         CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->att, e->q_cols, Ly.wo, p));
       }
-      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, ysrc, Ly.g_post_attn, M, H, c.rms_norm_eps, ns, static_cast<size_t>(128) * H);
-      CK(cudaGetLastError());
+      CK(launch_k(add_rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->x, ysrc, static_cast<const float*>(Ly.g_post_attn), M, H,
+                  c.rms_norm_eps, ns, static_cast<size_t>(128) * H));
       e->st.launches++;
       CKR(rmsnorm(e, st, e->x, Ly.g_pre_ffn, e->xn, nullptr, M));
     }
@@ -867,8 +883,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
         p.out = e->y; p.ldo = H;
         CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->hb, I, Ly.wd, p));
       }
-      add_rmsnorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(e->x, ysrc, Ly.g_post_ffn, M, H, c.rms_norm_eps, ns, static_cast<size_t>(128) * H);
-      CK(cudaGetLastError());
+      CK(launch_k(add_rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->x, ysrc, static_cast<const float*>(Ly.g_post_ffn), M, H,
+                  c.rms_norm_eps, ns, static_cast<size_t>(128) * H));
       e->st.launches++;
     }
   }
@@ -892,8 +908,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
         CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, nullptr, M, pend));
         pend = 0;
       }
-      gather_last_kernel<<<B, 256, 0, st>>>(e->x, e->xl, B, S, H);
-      CK(cudaGetLastError());
+      CK(launch_k(gather_last_kernel, dim3(B), dim3(256), 0, st, static_cast<const float*>(e->x), e->xl, B, S, H));
       e->st.launches++;
       CKR(rmsnorm(e, st, e->xl, e->g_final, e->xnl, nullptr, B));
       a = e->xnl;
@@ -903,8 +918,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     p.out = logits; p.ldo = c.vocab_size; p.softcap = c.final_logit_softcap;
     CKR(eng_gemm(e, st, B <= 128 ? 128 : 256, EPI_F32, a, H, e->embed, p, lda_rows ? e->ws_batch : e->ws_tokens));
   }
-  add_scalar_kernel<<<1, 32, 0, st>>>(cache->t0_dev, S);
-  CK(cudaGetLastError());
+  CK(launch_k(add_scalar_kernel, dim3(1), dim3(32), 0, st, cache->t0_dev, S));
   e->st.launches++;
   return B2_OK;
 }
@@ -948,8 +962,7 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
     if (it == e->graphs.end()) {
       // warm-up launch outside capture creates every descriptor / function attribute, then restore t0
       CKR(run_layers(e, kc, st, ids, B, S, logits_mode, logits, nullptr));
-      add_scalar_kernel<<<1, 32, 0, st>>>(kc->t0_dev, -S);
-      CK(cudaGetLastError());
+      CK(launch_k(add_scalar_kernel, dim3(1), dim3(32), 0, st, kc->t0_dev, -S));
       CK(cudaStreamSynchronize(st));
       // the legacy default stream cannot be captured: record on the engine's own stream, replay on `st`
       cudaStream_t cs = e->stream;

@@ -301,10 +301,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; operands are only touched below
 
   auto tile_coords = [&](int tile, int& mb, int& nb, int& kb0) {
     kb0 = (tile % p.split_k) * KB;
