@@ -49,7 +49,9 @@ typedef struct b2_config {
   int32_t sliding_window;       /* HF Gemma-2: 4096 on even layers */
   float attn_scale;             /* 0 = 1/sqrt(head_dim) (what the reference does) */
   int32_t always_causal;        /* 0 = reference quirk: no mask when q_len <= 2 (llama3.2_model_numpy.py:479) */
-  int32_t precise;              /* reserved: hi/lo split-bf16 parity mode */
+  int32_t precise;              /* 1: parity mode -- every bf16 activation is carried as hi+lo bf16 planes (exact weights,
+                                   2x-K weight GEMMs, 3 MMAs per attention product): logits within 1e-2 of the
+                                   reference at ~3x the cost; head_dim 64/128 only */
 } b2_config;
 
 typedef struct b2_engine b2_engine;

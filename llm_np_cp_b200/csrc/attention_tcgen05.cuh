@@ -28,18 +28,24 @@ struct AttnParams {
   __nv_bfloat16* out;    // [B*S, NH*HD]
   int ldo;
   int v_lbo, v_sbo;      // V (MN-major) descriptor byte offsets; 0 = defaults (BNKV*128, 1024)
+  // precise (hi/lo split-bf16) mode: every bf16 operand x is carried as x_hi + x_lo
+  int q_lo_col;          // column offset of the lo plane inside a q row (= NH*HD), 0 = not precise
+  int kv_lo_row;         // row offset of the lo plane inside the K/V tensor maps (= B_max*NKV*Tmax)
+  int out_lo_col;        // column offset of the lo plane inside an output row
 };
 
 constexpr int ATT_BM = 128;
 constexpr int ATT_THREADS = 192;
 
-template <int HD>
+// NP = operand planes: 1 = plain bf16, 2 = precise mode (hi and lo planes of Q, K, V and P; three MMAs per product:
+// hi.hi + hi.lo + lo.hi)
+template <int HD, int NP = 1>
 struct AttnCfg {
-  static constexpr int BNKV = (HD <= 128) ? 128 : 64;
+  static constexpr int BNKV = (NP == 2) ? 64 : ((HD <= 128) ? 128 : 64);
   static constexpr int KV_STAGES = 2;
-  static constexpr int Q_BYTES = ATT_BM * HD * 2;
-  static constexpr int KV_BYTES = BNKV * HD * 2;       // one K or V tile
-  static constexpr int P_BYTES = ATT_BM * BNKV * 2;
+  static constexpr int Q_BYTES = NP * ATT_BM * HD * 2;
+  static constexpr int KV_BYTES = NP * BNKV * HD * 2;  // one K or V tile (all planes)
+  static constexpr int P_BYTES = NP * ATT_BM * BNKV * 2;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + P_BYTES + BAR_BYTES + 768;
   static constexpr int TMEM_USED = BNKV + HD;
@@ -73,7 +79,8 @@ __device__ __forceinline__ void att_max32(const uint32_t (&sr)[32], int rel, uns
 // bf16 P -> 128B-swizzled smem row (the K-major A operand of P.V); accumulates the fp32 row sum.
 template <bool MASK, bool CAP>
 __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8_t* sP, int r, float sl2, float m_safe,
-                                          float cap_in, float cap_out, int lo, unsigned span, float (&sum)[4]) {
+                                          float cap_in, float cap_out, int lo, unsigned span, float (&sum)[4],
+                                          uint8_t* sPlo = nullptr) {
   const int rel = c * 32 - lo;
   float e[32];
 #pragma unroll
@@ -103,6 +110,22 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
     const int chunk16 = (c & 1) * 4 + i;
     *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
   }
+  if (sPlo) {   // precise mode: P_lo = bf16(P - bf16(P))
+    uint8_t* lrow = sPlo + (c >> 1) * (ATT_BM * 128) + r * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float d[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = e[8 * i + k] - __bfloat162float(__float2bfloat16_rn(e[8 * i + k]));
+      uint4 u;
+      u.x = pack_bf16(d[0], d[1]);
+      u.y = pack_bf16(d[2], d[3]);
+      u.z = pack_bf16(d[4], d[5]);
+      u.w = pack_bf16(d[6], d[7]);
+      const int chunk16 = (c & 1) * 4 + i;
+      *reinterpret_cast<uint4*>(lrow + ((chunk16 ^ (r & 7)) << 4)) = u;
+    }
+  }
 }
 
 // One kv tile of the online softmax for one q row, SINGLE pass over TMEM: the whole S row (SCH*32 fp32) is read
@@ -111,10 +134,10 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
 // S lives at tS_row, O at tO_row (TMEM, this thread's lane), P goes to sP (smem, 128B-swizzled rows).
 template <int SCH, bool MASK, bool CAP>
 __device__ __forceinline__ float att_exp_regs(uint32_t (&x)[SCH][32], uint8_t* sP, int r, float sl2, float m_safe,
-                                              float cap_in, float cap_out, int lo, unsigned span) {
+                                              float cap_in, float cap_out, int lo, unsigned span, uint8_t* sPlo) {
   float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < SCH; ++c) att_exp32<MASK, CAP>(x[c], c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum);
+  for (int c = 0; c < SCH; ++c) att_exp32<MASK, CAP>(x[c], c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum, sPlo);
   return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
@@ -122,7 +145,7 @@ template <int SCH, int OCH>
 __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_row, uint8_t* sP, int r, bool need_mask,
                                                  int lo, unsigned span, bool cap, float sl2, float cap_in, float cap_out,
                                                  float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity,
-                                                 uint64_t* bar_sfree) {
+                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr) {
   constexpr float TAU = 8.0f;   // lazy-rescale threshold (log2 units): P stays <= 2^8
   uint32_t x[SCH][32];
 #pragma unroll
@@ -168,18 +191,19 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
   const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
   float lsum;
   if (cap) {
-    lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
-                     : att_exp_regs<SCH, false, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
+    lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo)
+                     : att_exp_regs<SCH, false, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo);
   } else {
-    lsum = need_mask ? att_exp_regs<SCH, true, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span)
-                     : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span);
+    lsum = need_mask ? att_exp_regs<SCH, true, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo)
+                     : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo);
   }
   l += lsum;
 }
 
 // O / l -> bf16 -> out row (the reference's transpose+reshape, llama3.2_model_numpy.py:509-511)
 template <int OCH>
-__device__ __forceinline__ void att_store_out(uint32_t tO_row, bool have_o, float l, bool row_ok, __nv_bfloat16* orow) {
+__device__ __forceinline__ void att_store_out(uint32_t tO_row, bool have_o, float l, bool row_ok, __nv_bfloat16* orow,
+                                              int lo_col = 0) {
   const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
 #pragma unroll 1
   for (int c = 0; c < OCH; ++c) {
@@ -203,15 +227,36 @@ __device__ __forceinline__ void att_store_out(uint32_t tO_row, bool have_o, floa
         u.w = pack_bf16(__uint_as_float(orr[8 * i + 6]) * inv_l, __uint_as_float(orr[8 * i + 7]) * inv_l);
         d[i] = u;
       }
+      if (lo_col) {   // precise mode: residual plane
+        uint4* dl = reinterpret_cast<uint4*>(orow + lo_col + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float f = __uint_as_float(orr[8 * i + k]) * inv_l;
+            v[k] = f - __bfloat162float(__float2bfloat16_rn(f));
+          }
+          uint4 u;
+          u.x = pack_bf16(v[0], v[1]);
+          u.y = pack_bf16(v[2], v[3]);
+          u.z = pack_bf16(v[4], v[5]);
+          u.w = pack_bf16(v[6], v[7]);
+          dl[i] = u;
+        }
+      }
     }
   }
 }
 
-template <int HD>
+template <int HD, int NP>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using Cfg = AttnCfg<HD>;
+  using Cfg = AttnCfg<HD, NP>;
+  constexpr int QP = ATT_BM * HD * 2;                  // bytes of one Q plane
+  constexpr int KP = Cfg::BNKV * HD * 2;               // bytes of one K / V plane of a stage
+  constexpr int PP = ATT_BM * Cfg::BNKV * 2;           // bytes of one P plane
   constexpr int BNKV = Cfg::BNKV;
   constexpr int HB = HD / 64;        // 64-column (128-byte) blocks per head
   constexpr int SCH = BNKV / 32;     // 32-column chunks of S per row
@@ -282,8 +327,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (elect_one()) {
       mbar_expect_tx(bar_q, Cfg::Q_BYTES);
 #pragma unroll
-      for (int hb = 0; hb < HB; ++hb)
-        tma_load_2d(sQ + hb * (ATT_BM * 128), &tmap_q, bar_q, h * HD + hb * 64, b * p.S + q0, kEvictFirst);
+      for (int pl = 0; pl < NP; ++pl)
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d(sQ + pl * QP + hb * (ATT_BM * 128), &tmap_q, bar_q, pl * p.q_lo_col + h * HD + hb * 64, b * p.S + q0,
+                      kEvictFirst);
       const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
       int stage = 0;
       uint32_t phase = 0;
@@ -291,14 +339,18 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mbar_wait(&kv_empty[stage], phase ^ 1);
         mbar_expect_tx(&k_full[stage], Cfg::KV_BYTES);
 #pragma unroll
-        for (int hb = 0; hb < HB; ++hb)
-          tma_load_2d(sK + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[stage], hb * 64,
-                      kv_row0 + j * BNKV, kEvictLast);
+        for (int pl = 0; pl < NP; ++pl)
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sK + stage * Cfg::KV_BYTES + pl * KP + hb * (BNKV * 128), &tmap_k, &k_full[stage], hb * 64,
+                        pl * p.kv_lo_row + kv_row0 + j * BNKV, kEvictLast);
         mbar_expect_tx(&v_full[stage], Cfg::KV_BYTES);
 #pragma unroll
-        for (int hb = 0; hb < HB; ++hb)
-          tma_load_2d(sV + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_v, &v_full[stage], hb * 64,
-                      kv_row0 + j * BNKV, kEvictLast);
+        for (int pl = 0; pl < NP; ++pl)
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sV + stage * Cfg::KV_BYTES + pl * KP + hb * (BNKV * 128), &tmap_v, &v_full[stage], hb * 64,
+                        pl * p.kv_lo_row + kv_row0 + j * BNKV, kEvictLast);
         if (++stage == Cfg::KV_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -316,31 +368,40 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int it = 0; it < n_tiles; ++it) {
         const uint32_t k_addr = smem_u32(sK + stage * Cfg::KV_BYTES);
         const uint32_t v_addr = smem_u32(sV + stage * Cfg::KV_BYTES);
-        // S = Q . K^T   (contraction over head_dim: HB swizzle atoms x 4 UMMA_K steps)
+        // S = Q . K^T   (contraction over head_dim: HB swizzle atoms x 4 UMMA_K steps); precise mode sums the three
+        // cross terms Qh.Kh + Qh.Kl + Ql.Kh into the same accumulator
         mbar_wait(&k_full[stage], phase);
         tc_fence_after();
 #pragma unroll
-        for (int hb = 0; hb < HB; ++hb) {
+        for (int term = 0; term < (NP == 2 ? 3 : 1); ++term) {
+          const int qa = (term == 2) ? 1 : 0, kb = (term == 1) ? 1 : 0;   // plane of Q / of K
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_smem_desc(smem_u32(sQ) + hb * (ATT_BM * 128) + k * 32, 16, 1024);
-            const uint64_t bd = umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024);
-            umma_bf16_ss(tS, ad, bd, idesc_s, (hb | k) != 0 ? 1u : 0u);
+          for (int hb = 0; hb < HB; ++hb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = umma_smem_desc(smem_u32(sQ) + qa * QP + hb * (ATT_BM * 128) + k * 32, 16, 1024);
+              const uint64_t bd = umma_smem_desc(k_addr + kb * KP + hb * (BNKV * 128) + k * 32, 16, 1024);
+              umma_bf16_ss(tS, ad, bd, idesc_s, (term | hb | k) != 0 ? 1u : 0u);
+            }
           }
         }
         umma_commit(bar_s);
-        // O += P . V    (contraction over the BNKV kv rows, 16 per UMMA)
+        // O += P . V    (contraction over the BNKV kv rows, 16 per UMMA); precise: Ph.Vh + Ph.Vl + Pl.Vh
         mbar_wait(bar_p, it & 1);
         mbar_wait(&v_full[stage], phase);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < BNKV / 16; ++kk) {
-          const uint64_t ad =
-              umma_smem_desc(smem_u32(sP) + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024);
-          // V tile: kv rows at 128 B pitch; 64-column head_dim blocks are BNKV*128 B apart (LBO)
-          const uint64_t bd = umma_smem_desc(v_addr + kk * (16 * 128), p.v_lbo ? p.v_lbo : BNKV * 128,
-                                             p.v_sbo ? p.v_sbo : 1024);
-          umma_bf16_ss(tO, ad, bd, idesc_o, (it | kk) != 0 ? 1u : 0u);
+        for (int term = 0; term < (NP == 2 ? 3 : 1); ++term) {
+          const int pa = (term == 2) ? 1 : 0, vb = (term == 1) ? 1 : 0;   // plane of P / of V
+#pragma unroll
+          for (int kk = 0; kk < BNKV / 16; ++kk) {
+            const uint64_t ad =
+                umma_smem_desc(smem_u32(sP) + pa * PP + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024);
+            // V tile: kv rows at 128 B pitch; 64-column head_dim blocks are BNKV*128 B apart (LBO)
+            const uint64_t bd = umma_smem_desc(v_addr + vb * KP + kk * (16 * 128), p.v_lbo ? p.v_lbo : BNKV * 128,
+                                               p.v_sbo ? p.v_sbo : 1024);
+            umma_bf16_ss(tO, ad, bd, idesc_o, (it | term | kk) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&kv_empty[stage]);
         umma_commit(bar_o);
@@ -377,7 +438,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(bar_s, it & 1);
       tc_fence_after();
       att_softmax_tile<SCH, OCH>(tS + lane_off, tO + lane_off, sP, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l,
-                                 it > 0, bar_o, (it - 1) & 1, nullptr);
+                                 it > 0, bar_o, (it - 1) & 1, nullptr, NP == 2 ? sP + PP : nullptr);
       fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the MMA
       tc_fence_before();
       mbar_arrive(bar_p);
@@ -388,7 +449,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tc_fence_after();
     }
     att_store_out<OCH>(tO + lane_off, n_tiles > 0, l, (q0 + r) < p.S,
-                       p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD);
+                       p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD, NP == 2 ? p.out_lo_col : 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -672,18 +733,19 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 }
 
 // ---------------------------------------------------------------------------------------------
-// Decode attention (q_len == 1): bandwidth-bound, CUDA cores.  One warp per (batch, q head).
-// A kv position is owned by LPP = HD/64 adjacent lanes (64 head-dim elements each, 16-byte loads);
-// 32/LPP positions are in flight per warp iteration, each lane group runs its own online softmax,
-// and the groups are merged with warp shuffles at the end.  Reference path:
-// llama3.2_model_numpy.py:470-511 with q_len = 1 (no mask branch, :479).
+// Decode attention (q_len == 1): bandwidth/latency-bound, CUDA cores.  One warp per (batch, q head).
+// A kv position is owned by LPP = HD/16 adjacent lanes (16 head-dim elements = two 16-byte loads each), so
+// 32/LPP positions are in flight per warp iteration and a K/V row is read as one contiguous 128..512-byte
+// segment by neighbouring lanes.  Each lane group runs its own online softmax; the groups are merged with
+// warp shuffles at the end.  Reference path: llama3.2_model_numpy.py:470-511 with q_len = 1 (no mask, :479).
 // ---------------------------------------------------------------------------------------------
 template <int HD>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kc,
                    const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int ldo, int B, int NH,
-                   int NKV, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap, int window) {
-  constexpr int LPP = HD / 64;                   // lanes per kv position
+                   int NKV, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap, int window,
+                   int q_lo_col, size_t kv_lo_off, int out_lo_col) {   // precise mode: lo planes (0 = plain bf16)
+  constexpr int LPP = HD / 16;                   // lanes per kv position (4 / 8 / 16)
   constexpr int PPI = 32 / LPP;                  // positions per warp iteration
   pdl_trigger();
   pdl_wait();
@@ -695,12 +757,13 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
   const int T = *t0_ptr + 1;                     // this step's token is already appended
   const int qpos = T - 1;
   const int kv_begin = (window > 0) ? max(0, qpos - window + 1) : 0;
-  const int slice = lane % LPP;                  // which 64-element slice of the head this lane owns
-  float qf[64];
+  const int slice = lane % LPP;                  // which 16-element slice of the head this lane owns
+  const int grp = lane / LPP;                    // which of the PPI positions of an iteration
+  float qf[16];
   {
-    const uint4* q4 = reinterpret_cast<const uint4*>(q + static_cast<size_t>(b) * ldq + h * HD + slice * 64);
+    const uint4* q4 = reinterpret_cast<const uint4*>(q + static_cast<size_t>(b) * ldq + h * HD + slice * 16);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 2; ++i) {
       const uint4 u = __ldg(q4 + i);
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -709,31 +772,63 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
         qf[8 * i + 2 * e] = f.x;
         qf[8 * i + 2 * e + 1] = f.y;
       }
-    }
-  }
-  const __nv_bfloat16* kbase = kc + static_cast<size_t>(b * NKV + kvh) * Tmax * HD + slice * 64;
-  const __nv_bfloat16* vbase = vc + static_cast<size_t>(b * NKV + kvh) * Tmax * HD + slice * 64;
-  const float LOG2E = 1.4426950408889634f;
-  float m = -INFINITY, l = 0.f;
-  float o[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) o[i] = 0.f;
-  for (int tb = kv_begin; tb < T; tb += PPI) {   // warp-uniform trip count
-    const int t = tb + lane / LPP;
-    const bool ok = t < T;
-    float s = 0.f;
-    if (ok) {
-      const uint4* k4 = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(t) * HD);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(k4 + i);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+      if (q_lo_col) {
+        const uint4 ul = __ldg(q4 + i + q_lo_col / 8);
+        const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ul);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(h2[e]);
+          const float2 f = __bfloat1622float2(l2[e]);
+          qf[8 * i + 2 * e] += f.x;
+          qf[8 * i + 2 * e + 1] += f.y;
+        }
+      }
+    }
+  }
+  const __nv_bfloat16* kbase = kc + static_cast<size_t>(b * NKV + kvh) * Tmax * HD + slice * 16;
+  const __nv_bfloat16* vbase = vc + static_cast<size_t>(b * NKV + kvh) * Tmax * HD + slice * 16;
+  const float LOG2E = 1.4426950408889634f;
+  float m = -INFINITY, l = 0.f;
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = 0.f;
+  for (int tb = kv_begin; tb < T; tb += PPI) {   // warp-uniform trip count
+    const int t = tb + grp;
+    const bool ok = t < T;
+    float s = 0.f;
+    uint4 kv[2], vv[2], vlo[2] = {};
+    if (ok) {
+      const uint4* k4 = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(t) * HD);
+      const uint4* v4 = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(t) * HD);
+      kv[0] = __ldg(k4);
+      kv[1] = __ldg(k4 + 1);
+      vv[0] = __ldg(v4);          // V issued together with K: one memory round trip per iteration
+      vv[1] = __ldg(v4 + 1);
+      uint4 kl[2] = {}, vl[2] = {};
+      if (kv_lo_off) {
+        kl[0] = __ldg(k4 + kv_lo_off / 8);
+        kl[1] = __ldg(k4 + kv_lo_off / 8 + 1);
+        vl[0] = __ldg(v4 + kv_lo_off / 8);
+        vl[1] = __ldg(v4 + kv_lo_off / 8 + 1);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[i]);
+        const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&kl[i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h2[e]);
+          if (kv_lo_off) {
+            const float2 g = __bfloat1622float2(l2[e]);
+            f.x += g.x;
+            f.y += g.y;
+          }
           s = fmaf(qf[8 * i + 2 * e], f.x, s);
           s = fmaf(qf[8 * i + 2 * e + 1], f.y, s);
         }
+      }
+      if (kv_lo_off) {   // fold V_lo into the registers holding V (as fp32 pairs below)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) vlo[i] = vl[i];
       }
     }
 #pragma unroll
@@ -746,14 +841,18 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
       const float alpha = fast_exp2(m - m_new);  // 0 on the first item (m = -inf)
       const float pexp = fast_exp2(s - m_new);
       l = l * alpha + pexp;
-      const uint4* v4 = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(t) * HD);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(v4 + i);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+      for (int i = 0; i < 2; ++i) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[i]);
+        const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&vlo[i]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(h2[e]);
+          float2 f = __bfloat1622float2(h2[e]);
+          if (kv_lo_off) {
+            const float2 g = __bfloat1622float2(l2[e]);
+            f.x += g.x;
+            f.y += g.y;
+          }
           o[8 * i + 2 * e] = fmaf(pexp, f.x, o[8 * i + 2 * e] * alpha);
           o[8 * i + 2 * e + 1] = fmaf(pexp, f.y, o[8 * i + 2 * e + 1] * alpha);
         }
@@ -771,22 +870,33 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
   for (int off = 16; off >= LPP; off >>= 1) l_all += __shfl_xor_sync(0xffffffffu, l_all, off);
   const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
+  for (int i = 0; i < 16; ++i) {
     float v = o[i] * w;
 #pragma unroll
     for (int off = 16; off >= LPP; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     o[i] = v * inv;
   }
   if (lane < LPP) {
-    uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * ldo + h * HD + slice * 64);
+    uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * ldo + h * HD + slice * 16);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 2; ++i) {
       uint4 u;
       u.x = pack_bf16(o[8 * i + 0], o[8 * i + 1]);
       u.y = pack_bf16(o[8 * i + 2], o[8 * i + 3]);
       u.z = pack_bf16(o[8 * i + 4], o[8 * i + 5]);
       u.w = pack_bf16(o[8 * i + 6], o[8 * i + 7]);
       d[i] = u;
+      if (out_lo_col) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = o[8 * i + k] - __bfloat162float(__float2bfloat16_rn(o[8 * i + k]));
+        uint4 ul;
+        ul.x = pack_bf16(v[0], v[1]);
+        ul.y = pack_bf16(v[2], v[3]);
+        ul.z = pack_bf16(v[4], v[5]);
+        ul.w = pack_bf16(v[6], v[7]);
+        d[i + out_lo_col / 8] = ul;
+      }
     }
   }
 }

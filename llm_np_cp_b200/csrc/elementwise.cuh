@@ -98,8 +98,8 @@ rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16
 // the partials as rmsnorm_kernel.
 __global__ void __launch_bounds__(256)
 rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
-                   float* __restrict__ out_f32, int H, float eps, const float* __restrict__ partials, int nsplit,
-                   size_t split_stride) {
+                   int ld_out, int lo_off, float* __restrict__ out_f32, int H, float eps,
+                   const float* __restrict__ partials, int nsplit, size_t split_stride) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[8];
@@ -145,8 +145,17 @@ rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bflo
     if (idx < nv4) {
       const float4 gg = __ldg(gr + idx);
       const float4 o = make_float4(v[i].x * rs * gg.x, v[i].y * rs * gg.y, v[i].z * rs * gg.z, v[i].w * rs * gg.w);
-      if (out_bf16)
-        *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * H + idx * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      if (out_bf16) {
+        __nv_bfloat16* d = out_bf16 + static_cast<size_t>(row) * ld_out + idx * 4;
+        *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        if (lo_off) {
+          const float lx = o.x - __bfloat162float(__float2bfloat16_rn(o.x));
+          const float ly = o.y - __bfloat162float(__float2bfloat16_rn(o.y));
+          const float lz = o.z - __bfloat162float(__float2bfloat16_rn(o.z));
+          const float lw = o.w - __bfloat162float(__float2bfloat16_rn(o.w));
+          *reinterpret_cast<uint2*>(d + lo_off) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
+        }
+      }
       if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * H)[idx] = o;
     }
   }

@@ -212,19 +212,19 @@ static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
   return fail(B2_ERR_ARG, "no GEMM instantiation for bn=%d epi=%d", bn, epi);
 }
 
-template <int HD>
+template <int HD, int NP>
 static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                          cudaStream_t st) {
-  auto kern = attn_prefill_kernel<HD>;
+  auto kern = attn_prefill_kernel<HD, NP>;
   static bool attr[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 16 || !attr[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<HD>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<HD, NP>::SMEM_BYTES));
     if (dev < 16) attr[dev] = true;
   }
   dim3 grid((p.S + ATT_BM - 1) / ATT_BM, p.NH, p.B);
-  CK(launch_k(kern, grid, dim3(ATT_THREADS), AttnCfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
+  CK(launch_k(kern, grid, dim3(ATT_THREADS), AttnCfg<HD, NP>::SMEM_BYTES, st, tq, tk, tv, p));
   return B2_OK;
 }
 
@@ -254,27 +254,34 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
   if (const char* ev = getenv("B2_V_LBO")) p.v_lbo = atoi(ev);   // bring-up knobs for the MN-major V descriptor
   if (const char* ev = getenv("B2_V_SBO")) p.v_sbo = atoi(ev);
   static const bool force_single = getenv("B2_ATTN_SINGLE") != nullptr;
-  const bool pair = !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
-  const uint64_t kv_rows = static_cast<uint64_t>(p.B) * p.NKV * p.Tmax;
-  const int bnkv = pair ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64);
-  CKR(make_tmap(&tq, q, static_cast<uint64_t>(p.B) * p.S, static_cast<uint64_t>(p.NH) * HD, ldq, ATT_BM));
+  const bool precise = p.q_lo_col != 0;
+  const bool pair = !precise && !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
+  const int planes = precise ? 2 : 1;
+  const uint64_t kv_rows = static_cast<uint64_t>(planes) * (precise ? p.kv_lo_row : static_cast<uint64_t>(p.B) * p.NKV * p.Tmax);
+  const int bnkv = precise ? 64 : (pair ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64));
+  CKR(make_tmap(&tq, q, static_cast<uint64_t>(p.B) * p.S, static_cast<uint64_t>(planes) * p.NH * HD, ldq, ATT_BM));
   CKR(make_tmap(&tk, kc, kv_rows, HD, HD, bnkv));
   CKR(make_tmap(&tv, vc, kv_rows, HD, HD, bnkv));
+  if (precise) {
+    if (HD == 64) return launch_attn_t<64, 2>(tq, tk, tv, p, st);
+    if (HD == 128) return launch_attn_t<128, 2>(tq, tk, tv, p, st);
+    return fail(B2_ERR_ARG, "precise mode supports head_dim 64 and 128 only");
+  }
   if (pair) return HD == 64 ? launch_attn_pair_t<64>(tq, tk, tv, p, st) : launch_attn_pair_t<128>(tq, tk, tv, p, st);
-  if (HD == 64) return launch_attn_t<64>(tq, tk, tv, p, st);
-  if (HD == 128) return launch_attn_t<128>(tq, tk, tv, p, st);
-  if (HD == 256) return launch_attn_t<256>(tq, tk, tv, p, st);
+  if (HD == 64) return launch_attn_t<64, 1>(tq, tk, tv, p, st);
+  if (HD == 128) return launch_attn_t<128, 1>(tq, tk, tv, p, st);
+  if (HD == 256) return launch_attn_t<256, 1>(tq, tk, tv, p, st);
   return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", HD);
 }
 
 static int attn_decode(const bf16* q, int ldq, const bf16* kc, const bf16* vc, bf16* out, int ldo, int B, int NH,
                        int NKV, int HD, int Tmax, const int* t0_ptr, float scale, float softcap, int window,
-                       cudaStream_t st) {
+                       cudaStream_t st, int q_lo_col = 0, size_t kv_lo_off = 0, int out_lo_col = 0) {
   const int grid = (B * NH + 3) / 4;
 #define DEC(HD_)                                                                                              \
   if (HD == HD_) {                                                                                            \
     CK(launch_k(attn_decode_kernel<HD_>, dim3(grid), dim3(128), 0, st, q, ldq, kc, vc, out, ldo, B, NH, NKV, Tmax, t0_ptr, \
-                scale, softcap, window));                                                                     \
+                scale, softcap, window, q_lo_col, kv_lo_off, out_lo_col));                                    \
     return B2_OK;                                                                                             \
   }
   DEC(64) DEC(128) DEC(256)
@@ -342,7 +349,8 @@ struct b2_cache {
   int max_batch, max_tokens, len;
   bf16* kv;      // [L][2][max_batch][NKV][max_tokens][HD]
   int* t0_dev;
-  size_t plane;  // elements per (layer, k|v)
+  size_t plane;  // elements per (layer, k|v) plane
+  int pf;        // planes per tensor: 1, or 2 in precise mode (hi plane followed by lo plane)
 };
 
 struct GraphKey {
@@ -426,6 +434,10 @@ static int pick_band(int N, int K) {
 static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* a, int lda, const bf16* w, GemmParams p,
                     int a_rows = 0, int c_rows = 0) {
   const CUtensorMap *ta, *tb, *tc;
+  if (e->cfg.precise) {   // A rows are [hi | lo]: contraction runs over 2K with the W k-coordinate wrapping at K
+    p.K = 2 * p.k_wrap;
+    lda *= 2;
+  }
   if (!a_rows) a_rows = e->ws_tokens > p.M ? e->ws_tokens : p.M;
   CKR(get_tmap(e, a, a_rows, p.K, lda, GEMM_BM, &ta));
   CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, bn, &tb));
@@ -458,6 +470,7 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
   if (c.intermediate_size % 64) return fail(B2_ERR_ARG, "intermediate_size %d must be a multiple of 64", c.intermediate_size);
   if (c.vocab_size % 32) return fail(B2_ERR_ARG, "vocab_size %d must be a multiple of 32", c.vocab_size);
   if (c.max_positions <= 0) return fail(B2_ERR_ARG, "max_positions must be positive");
+  if (c.precise && c.head_dim == 256) return fail(B2_ERR_ARG, "precise (hi/lo split) mode supports head_dim 64 and 128 only");
   CK(cudaSetDevice(device));
   b2_engine* e = new b2_engine();
   e->cfg = c;
@@ -662,7 +675,9 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   c->max_tokens = max_tokens;
   c->len = 0;
   c->plane = static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * max_tokens * e->cfg.head_dim;
-  const size_t bytes = c->plane * 2 * e->cfg.num_hidden_layers * 2;
+  c->pf = e->cfg.precise ? 2 : 1;
+  const size_t bytes = c->plane * c->pf * 2 * e->cfg.num_hidden_layers * 2;
+  if (c->pf == 2 && c->plane > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "precise-mode cache plane too large"); }
   CK(cudaMalloc(&c->kv, bytes));
   CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
   CK(cudaMalloc(&c->t0_dev, 4));
@@ -682,8 +697,8 @@ extern "C" int b2_cache_reset(b2_cache* c) {
   CK(cudaDeviceSynchronize());
   return B2_OK;
 }
-static bf16* cache_k(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2) * c->plane; }
-static bf16* cache_v(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2 + 1) * c->plane; }
+static bf16* cache_k(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2) * c->pf * c->plane; }
+static bf16* cache_v(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2 + 1) * c->pf * c->plane; }
 
 extern "C" int b2_cache_read(const b2_cache* c, int layer, int which, int batch, void* dev_out) {
   if (!c || !dev_out || layer < 0 || layer >= c->e->cfg.num_hidden_layers || batch <= 0 || batch > c->max_batch)
@@ -711,14 +726,15 @@ static int ensure_ws(b2_engine* e, int M, int B) {
   const size_t Mp = M > e->ws_tokens ? M : e->ws_tokens, Bp = B > e->ws_batch ? B : e->ws_batch;
   CK(cudaMalloc(&e->x, Mp * H * 4));
   if (c.gemma) CK(cudaMalloc(&e->y, Mp * H * 4));
-  CK(cudaMalloc(&e->xn, Mp * H * 2));
-  CK(cudaMalloc(&e->q, Mp * e->q_cols * 2));
-  CK(cudaMalloc(&e->att, Mp * e->q_cols * 2));
-  CK(cudaMalloc(&e->hb, Mp * I * 2));
+  const size_t pf = c.precise ? 2 : 1;   // precise mode: every bf16 activation row is [hi | lo]
+  CK(cudaMalloc(&e->xn, Mp * H * 2 * pf));
+  CK(cudaMalloc(&e->q, Mp * e->q_cols * 2 * pf));
+  CK(cudaMalloc(&e->att, Mp * e->q_cols * 2 * pf));
+  CK(cudaMalloc(&e->hb, Mp * I * 2 * pf));
   CK(cudaMalloc(&e->ids_ws, Mp * 8));
   CK(cudaMalloc(&e->xl, Bp * H * 4));
   CK(cudaMalloc(&e->part, static_cast<size_t>(MAX_SPLIT) * 128 * H * 4));
-  CK(cudaMalloc(&e->xnl, Bp * H * 2));
+  CK(cudaMalloc(&e->xnl, Bp * H * 2 * pf));
   e->ws_tokens = static_cast<int>(Mp);
   e->ws_batch = static_cast<int>(Bp);
   return B2_OK;
@@ -726,15 +742,16 @@ static int ensure_ws(b2_engine* e, int M, int B) {
 
 // nsplit > 0: first fold the pending split-K partials of the previous o_proj / down_proj into x
 static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16* ob, float* of, int M, int nsplit = 0) {
+  const int H = e->cfg.hidden_size, pf = e->cfg.precise ? 2 : 1;
+  const int ld = pf * H, lo = e->cfg.precise ? H : 0;   // precise: [hi | lo] rows
+  e->st.launches++;
   if (M <= 128) {   // decode / tiny prompts: a CTA per row keeps every load of the row in flight
-    CK(launch_k(rmsnorm_row_kernel, dim3(M), dim3(256), 0, st, x, g, ob, of, e->cfg.hidden_size, e->cfg.rms_norm_eps,
-                static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * e->cfg.hidden_size));
-    e->st.launches++;
+    CK(launch_k(rmsnorm_row_kernel, dim3(M), dim3(256), 0, st, x, g, ob, ld, lo, of, H, e->cfg.rms_norm_eps,
+                static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * H));
     return B2_OK;
   }
-  CK(launch_k(rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, g, ob, e->cfg.hidden_size, 0, of, M, e->cfg.hidden_size,
-              e->cfg.rms_norm_eps, static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * e->cfg.hidden_size));
-  e->st.launches++;
+  CK(launch_k(rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, g, ob, ld, lo, of, M, H, e->cfg.rms_norm_eps,
+              static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * H));
   return B2_OK;
 }
 
@@ -775,6 +792,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
   const b2_config& c = e->cfg;
   const int M = B * S, H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, HD = c.head_dim;
   const bool decode = (S == 1);
+  const int pf = c.precise ? 2 : 1;            // bf16 activation rows are [hi | lo] in precise mode
   const bool skinny = M <= 128 && !hidden;     // few rows: split-K so the weight stream covers all SMs
   int pend = 0;                                // split-K partials of the last down_proj not yet folded into x
   const float escale = c.gemma ? sqrtf(static_cast<float>(H)) : 1.0f;
@@ -797,7 +815,9 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
       p.Tmax = cache->max_tokens;
       p.nkv = c.num_key_value_heads;
       p.q_out = e->q;
-      p.ldq = e->q_cols;
+      p.ldq = pf * e->q_cols;
+      p.lo_off = c.precise ? e->q_cols : 0;
+      p.kv_lo_off = c.precise ? static_cast<int>(cache->plane) : 0;
       p.k_cache = cache_k(cache, li);
       p.v_cache = cache_v(cache, li);
       p.t0_ptr = cache->t0_dev;
@@ -807,19 +827,25 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     }
     const int window = (c.sliding_window > 0 && (li % 2 == 0)) ? c.sliding_window : 0;
     if (decode) {
-      CKR(attn_decode(e->q, e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, e->q_cols, B, c.num_attention_heads,
-                      c.num_key_value_heads, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st));
+      CKR(attn_decode(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, pf * e->q_cols, B, c.num_attention_heads,
+                      c.num_key_value_heads, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st,
+                      c.precise ? e->q_cols : 0, c.precise ? cache->plane : 0, c.precise ? e->q_cols : 0));
       e->st.launches++;
     } else {
       AttnParams a;
       memset(&a, 0, sizeof(a));
       a.B = B; a.S = S; a.NH = c.num_attention_heads; a.NKV = c.num_key_value_heads; a.Tmax = cache->max_tokens;
       a.t0_ptr = cache->t0_dev; a.scale = scale; a.softcap = c.attn_logit_softcap; a.causal = causal; a.window = window;
-      a.out = e->att; a.ldo = e->q_cols;
+      a.out = e->att; a.ldo = pf * e->q_cols;
+      if (c.precise) {
+        a.q_lo_col = e->q_cols;
+        a.out_lo_col = e->q_cols;
+        a.kv_lo_row = cache->max_batch * c.num_key_value_heads * cache->max_tokens;
+      }
       const double T = cache->len + S;
       const double pairs = causal ? (static_cast<double>(S) * (S + 1) / 2 + static_cast<double>(S) * cache->len) : S * T;
       time_begin(e, st, 4.0 * B * c.num_attention_heads * HD * pairs, 1);
-      int r = attn_prefill(e->q, e->q_cols, cache_k(cache, li), cache_v(cache, li), a, HD, st);
+      int r = attn_prefill(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), a, HD, st);
       time_end(e, st);
       CKR(r);
       e->st.launches++;
@@ -857,7 +883,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     }
     {
       GemmParams p = base_params(M, 2 * I, H);
-      p.out = e->hb; p.ldo = I; p.act = c.hidden_act;
+      p.out = e->hb; p.ldo = pf * I; p.act = c.hidden_act;
+      p.lo_off = c.precise ? I : 0;
       CKR(eng_gemm(e, st, pick_bn(M, 2 * I, 0), EPI_GLU, e->xn, H, Ly.wgu, p));           // act(gate)*up
     }
     if (!c.gemma) {

@@ -161,3 +161,49 @@ def test_forward_host_and_sampling():
     t = M.min_p_sampling(big, 0.1, generator=g, model=model).cpu().numpy()
     np.add.at(cnt, t, 1)
     assert np.abs(cnt / 2048 - want[0]).max() < 0.06
+
+
+# ---------------------------------------------------------------------------------------------
+# Precise (hi/lo split-bf16) parity mode: BASELINE.json's literal target -- logits within 1e-2 max-abs of
+# the reference's NumPy path.  Same kernels, every bf16 activation carried as hi + lo planes.
+# ---------------------------------------------------------------------------------------------
+PRECISE_TOL = 1e-2
+
+
+@pytest.mark.parametrize("name", ["llama_tiny_prefill", "llama_tiny128_prefill", "llama_tiny_long", "llama_tiny_qlen2"])
+def test_precise_prefill_within_1e2_of_reference(name):
+    meta, arr = load_golden(name)
+    cfg, w, model = build(meta, precise=True)
+    _, logits, _, hs, _ = model(arr["ids"], use_cache=False)
+    d = np.abs(logits.cpu().numpy().astype(np.float64) - arr["logits"])
+    print(f"[parity-precise] {name}: max_abs={d.max():.3g} mean_abs={d.mean():.3g}")
+    assert d.max() <= PRECISE_TOL
+    for i, h in enumerate(hs):
+        assert np.abs(h.cpu().numpy() - arr["hidden"][i]).max() <= PRECISE_TOL
+
+
+def test_precise_decode_within_1e2_of_reference():
+    meta, arr = load_golden("llama_tiny_decode")
+    cfg, w, model = build(meta, precise=True)
+    S, dec = meta["S"], meta["decode_steps"]
+    cache = M.KVCache(max_tokens=64)
+    _, logits, _, _, _ = model(arr["ids"][:, :S], use_cache=True, kv_cache=cache)
+    assert np.abs(logits.cpu().numpy() - arr["logits"]).max() <= PRECISE_TOL
+    for i in range(dec):
+        _, lg, _, _, _ = model(arr["ids"][:, S + i:S + i + 1], use_cache=True, kv_cache=cache, output_hidden_states=False)
+        d = np.abs(lg.cpu().numpy() - arr["decode_logits"][i]).max()
+        print(f"[parity-precise] decode step {i}: max_abs={d:.3g}")
+        assert d <= PRECISE_TOL
+
+
+def test_precise_llama_1b_config1_within_1e2():
+    """BASELINE.json config #1 at the literal 1e-2 max-abs tolerance (logit std 0.9)."""
+    meta, arr = load_golden("llama_1b_s16")
+    cfg, w, model = build(meta, precise=True)
+    _, logits, _, _, _ = model(arr["ids"], use_cache=False, output_hidden_states=False)
+    lg = logits.cpu().numpy().astype(np.float64)
+    d1 = np.abs(lg[:, :, ::61] - arr["logits_sub"]).max()
+    d2 = np.abs(lg[:, -1, :] - arr["logits_last"]).max()
+    print(f"[parity-precise] 1B config #1: max_abs sub={d1:.3g} last={d2:.3g}")
+    assert max(d1, d2) <= PRECISE_TOL
+    assert (lg.argmax(-1) == arr["argmax"]).all()
