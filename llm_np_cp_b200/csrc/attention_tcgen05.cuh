@@ -32,6 +32,24 @@ struct AttnParams {
   int q_lo_col;          // column offset of the lo plane inside a q row (= NH*HD), 0 = not precise
   int kv_lo_row;         // row offset of the lo plane inside the K/V tensor maps (= B_max*NKV*Tmax)
   int out_lo_col;        // column offset of the lo plane inside an output row
+  unsigned long long* trace;   // bring-up: clock64() timeline of CTA (0,0,0); nullptr = off
+};
+
+// timeline tracing (diagnostics only): role r of CTA (0,0,0) appends (event id, clock) pairs to trace[r*1024 ...]
+struct AttTrace {
+  unsigned long long* buf;
+  int n;
+  __device__ __forceinline__ void init(unsigned long long* t, int role) {
+    buf = (t && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? t + role * 1024 : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void ev(int id) {
+    if (buf && n < 510) {
+      buf[2 * n] = static_cast<unsigned long long>(id);
+      buf[2 * n + 1] = static_cast<unsigned long long>(clock64());
+      ++n;
+    }
+  }
 };
 
 constexpr int ATT_BM = 128;
@@ -145,7 +163,7 @@ template <int SCH, int OCH>
 __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_row, uint8_t* sP, int r, bool need_mask,
                                                  int lo, unsigned span, bool cap, float sl2, float cap_in, float cap_out,
                                                  float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity,
-                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr) {
+                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr, AttTrace* tr = nullptr) {
   constexpr float TAU = 8.0f;   // lazy-rescale threshold (log2 units): P stays <= 2^8
   uint32_t x[SCH][32];
 #pragma unroll
@@ -155,6 +173,7 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
     tc_fence_before();
     mbar_arrive(bar_sfree);
   }
+  if (tr) tr->ev(32);
   float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   if (need_mask) {
 #pragma unroll
@@ -171,9 +190,11 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
     if (m_used != -INFINITY) alpha = fast_exp2(m_used - m_tile);
     if (m_tile != -INFINITY) m_used = m_tile;
   }
+  if (tr) tr->ev(33);
   if (have_o) {
     mbar_wait(bar_o, o_parity);                    // previous P.V finished: O readable, sP reusable
     tc_fence_after();
+    if (tr) tr->ev(34);
     if (__any_sync(0xffffffffu, alpha != 1.0f)) {
       l *= alpha;
 #pragma unroll 1
@@ -477,6 +498,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // ---------------------------------------------------------------------------------------------
 constexpr int ATT2_THREADS = 384;
 
+
 template <int HD>
 struct Attn2Cfg {
   static constexpr int BNKV = (HD == 64) ? 128 : 64;
@@ -630,7 +652,11 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                          umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (!first || kk != 0) ? 1u : 0u);
           umma_commit(&o_done[g]);
         };
+        AttTrace tr;
+        tr.init(p.trace, 0);
+        tr.ev(0);
         mbar_wait(bar_q, 0);
+        tr.ev(1);
         int stage = 0;                       // ring slot of kv tile j
         uint32_t phase = 0;
         uint32_t nt[2] = {0, 0};             // kv tiles already handled per q tile (parity of s_free / p_ready)
@@ -651,10 +677,12 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const bool cur = j >= jb[g] && j < je[g], nxt = j + 1 >= jb[g] && j + 1 < je[g];
             if (nxt) {
               if (cur) mbar_wait(&s_free[g], nt[g] & 1);
+              tr.ev(10 + g);
               if (!k_next_ready) {
                 mbar_wait(&k_full[nstage], nphase);
                 k_next_ready = true;
               }
+              tr.ev(12 + g);
               tc_fence_after();
               issue_s(g, nstage);
             }
@@ -665,12 +693,14 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           for (int g = 0; g < 2; ++g) {
             if (j >= jb[g] && j < je[g]) {
               mbar_wait(&p_ready[g], nt[g] & 1);
+              tr.ev(20 + g);
               if (!v_ready) {
                 mbar_wait(&v_full[stage], phase);
                 v_ready = true;
               }
               tc_fence_after();
               issue_pv(g, stage, nt[g] == 0);
+              tr.ev(22 + g);
               ++nt[g];
             }
           }
@@ -697,6 +727,8 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const float cap_in = cap ? p.scale / p.softcap : 0.f, cap_out = p.softcap * LOG2E;
     float m_used = -INFINITY, l = 0.f;
     const int n_tiles = je[g] - jb[g];
+    AttTrace tr;
+    tr.init(((warp & 3) == 0 && lane == 0) ? p.trace : nullptr, 1 + g);
     for (int it = 0; it < n_tiles; ++it) {
       const int kv0 = (jb[g] + it) * BNKV;
       const bool need_mask = (p.causal && kv0 + BNKV - 1 > t0 + q0) || (kv0 + BNKV > T) ||
@@ -709,13 +741,16 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (p.window > 0) lo = max(0, qpos - p.window + 1 - kv0);
       }
       const unsigned span = hi > lo ? static_cast<unsigned>(hi - lo) : 0u;
+      tr.ev(30);
       mbar_wait(&s_full[g], it & 1);
+      tr.ev(31);
       tc_fence_after();
       att_softmax_tile<SCH, OCH>(tS_row, tO_row, sPg, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l, it > 0,
-                                 &o_done[g], (it - 1) & 1, &s_free[g]);
+                                 &o_done[g], (it - 1) & 1, &s_free[g], nullptr, &tr);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[g]);
+      tr.ev(35);
     }
     if (n_tiles > 0) {
       mbar_wait(&o_done[g], (n_tiles - 1) & 1);

@@ -253,6 +253,7 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
   AttnParams p = p_in;
   if (const char* ev = getenv("B2_V_LBO")) p.v_lbo = atoi(ev);   // bring-up knobs for the MN-major V descriptor
   if (const char* ev = getenv("B2_V_SBO")) p.v_sbo = atoi(ev);
+  if (const char* ev = getenv("B2_ATT_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(ev, nullptr, 0));   // device pointer (diagnostics)
   static const bool force_single = getenv("B2_ATTN_SINGLE") != nullptr;
   const bool precise = p.q_lo_col != 0;
   const bool pair = !precise && !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
