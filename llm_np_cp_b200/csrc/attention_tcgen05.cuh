@@ -657,56 +657,59 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tr.ev(0);
         mbar_wait(bar_q, 0);
         tr.ev(1);
-        int stage = 0;                       // ring slot of kv tile j
-        uint32_t phase = 0;
-        uint32_t nt[2] = {0, 0};             // kv tiles already handled per q tile (parity of s_free / p_ready)
+        auto has = [&](int g, int j) { return j >= jb[g] && j < je[g]; };
+        auto st_of = [&](int j) { return (j - j_lo) % ST; };
+        auto ph_of = [&](int j) { return static_cast<uint32_t>(((j - j_lo) / ST) & 1); };
         if (j_lo < j_hi) {
           mbar_wait(&k_full[0], 0);
           tc_fence_after();
 #pragma unroll
           for (int g = 0; g < 2; ++g)
-            if (j_lo >= jb[g] && j_lo < je[g]) issue_s(g, 0);
+            if (has(g, j_lo)) issue_s(g, 0);
         }
-        for (int j = j_lo; j < j_hi; ++j) {
-          const int nstage = (stage + 1 == ST) ? 0 : stage + 1;
-          const uint32_t nphase = (stage + 1 == ST) ? (phase ^ 1) : phase;
-          bool k_next_ready = false;
-          // (1) next scores, as soon as the current ones have been copied to registers
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const bool cur = j >= jb[g] && j < je[g], nxt = j + 1 >= jb[g] && j + 1 < je[g];
-            if (nxt) {
-              if (cur) mbar_wait(&s_free[g], nt[g] & 1);
-              tr.ev(10 + g);
-              if (!k_next_ready) {
-                mbar_wait(&k_full[nstage], nphase);
-                k_next_ready = true;
-              }
-              tr.ev(12 + g);
-              tc_fence_after();
-              issue_s(g, nstage);
-            }
+        // Skewed schedule: q tile 1 runs half an iteration behind q tile 0, so the exponentials (MUFU) of one tile
+        // overlap the TMEM loads / row max / waits of the other instead of both fighting for the XU pipe at once.
+        //   per kv tile j:  S0(j+1) | PV1(j-1) | S1(j+1) | PV0(j)
+        for (int j = j_lo; j <= j_hi; ++j) {
+          // (1) q tile 0: next scores as soon as the current ones are in registers
+          if (has(0, j + 1)) {
+            if (has(0, j)) mbar_wait(&s_free[0], (j - jb[0]) & 1);
+            tr.ev(10);
+            mbar_wait(&k_full[st_of(j + 1)], ph_of(j + 1));
+            tr.ev(12);
+            tc_fence_after();
+            issue_s(0, st_of(j + 1));
           }
-          // (2) P.V of this kv tile
-          bool v_ready = false;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (j >= jb[g] && j < je[g]) {
-              mbar_wait(&p_ready[g], nt[g] & 1);
-              tr.ev(20 + g);
-              if (!v_ready) {
-                mbar_wait(&v_full[stage], phase);
-                v_ready = true;
-              }
-              tc_fence_after();
-              issue_pv(g, stage, nt[g] == 0);
-              tr.ev(22 + g);
-              ++nt[g];
-            }
+          // (2) q tile 1: P.V of the previous kv tile; it is the last reader of that ring slot
+          if (j > j_lo && has(1, j - 1)) {
+            mbar_wait(&p_ready[1], (j - 1 - jb[1]) & 1);
+            tr.ev(21);
+            mbar_wait(&v_full[st_of(j - 1)], ph_of(j - 1));
+            tc_fence_after();
+            issue_pv(1, st_of(j - 1), j - 1 == jb[1]);
+            tr.ev(23);
+            umma_commit(&kv_empty[st_of(j - 1)]);
           }
-          umma_commit(&kv_empty[stage]);                  // every MMA reading K_j / V_j has been issued
-          stage = nstage;
-          phase = nphase;
+          if (j == j_hi) break;
+          // (3) q tile 1: next scores
+          if (has(1, j + 1)) {
+            if (has(1, j)) mbar_wait(&s_free[1], (j - jb[1]) & 1);
+            tr.ev(11);
+            mbar_wait(&k_full[st_of(j + 1)], ph_of(j + 1));
+            tr.ev(13);
+            tc_fence_after();
+            issue_s(1, st_of(j + 1));
+          }
+          // (4) q tile 0: P.V of this kv tile
+          if (has(0, j)) {
+            mbar_wait(&p_ready[0], (j - jb[0]) & 1);
+            tr.ev(20);
+            mbar_wait(&v_full[st_of(j)], ph_of(j));
+            tc_fence_after();
+            issue_pv(0, st_of(j), j == jb[0]);
+            tr.ev(22);
+            if (!has(1, j)) umma_commit(&kv_empty[st_of(j)]);   // q tile 1 does not read this kv tile
+          }
         }
       }
     }
