@@ -36,35 +36,22 @@ constexpr int NORM_MAXV = 24;  // float4 per lane: supports H <= 3072
 // (1 + gamma) for Gemma-2, gemma2_model.py:334).  One warp per row; the row stays in registers between the
 // reduction and the scaling pass.  Writes bf16 (the next GEMM's A operand; optional "lo" plane at
 // +lo_off columns for the precise mode) and/or fp32 (hidden-state capture / final norm).
-// Optional split-K epilogue of the previous GEMM: x[row] += sum_s partials[s][row] (fixed order => deterministic),
-// written back to x before normalising (decode path: o_proj / down_proj partial products).
 __global__ void __launch_bounds__(256)
-rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
-               int ld_out, int lo_off, float* __restrict__ out_f32, int M, int H, float eps,
-               const float* __restrict__ partials, int nsplit, size_t split_stride) {
+rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
+               int ld_out, int lo_off, float* __restrict__ out_f32, int M, int H, float eps) {
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= M) return;
   const int nv = H >> 7;  // float4 per lane
-  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H);
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * H);
   float4 v[NORM_MAXV];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NORM_MAXV; ++i) {
     if (i < nv) {
       v[i] = xr[i * 32 + lane];
-      if (nsplit > 0) {
-        for (int s = 0; s < nsplit; ++s) {
-          const float4 pp = reinterpret_cast<const float4*>(partials + s * split_stride + static_cast<size_t>(row) * H)[i * 32 + lane];
-          v[i].x += pp.x;
-          v[i].y += pp.y;
-          v[i].z += pp.z;
-          v[i].w += pp.w;
-        }
-        xr[i * 32 + lane] = v[i];
-      }
       ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     }
   }
@@ -93,7 +80,8 @@ rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16
   }
 }
 
-// Few-row variant (decode, M <= 128): one 256-thread CTA per row so the row's loads (and the split-K partials)
+// Few-row variant (decode, M <= 128): one 256-thread CTA per row so the row's loads (and the split-K partials of the
+// preceding o_proj / down_proj GEMM: x[row] += sum_s partials[s][row], fixed order => deterministic)
 // are all in flight at once instead of serialised inside a single warp.  Same arithmetic and summation order of
 // the partials as rmsnorm_kernel.
 __global__ void __launch_bounds__(256)

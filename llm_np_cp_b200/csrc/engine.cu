@@ -751,8 +751,9 @@ static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16
                 static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * H));
     return B2_OK;
   }
-  CK(launch_k(rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, g, ob, ld, lo, of, M, H, e->cfg.rms_norm_eps,
-              static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * H));
+  if (nsplit) return fail(B2_ERR_STATE, "split-K partials are only folded on the few-row path");
+  CK(launch_k(rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, static_cast<const float*>(x), g, ob, ld, lo, of, M, H,
+              e->cfg.rms_norm_eps));
   return B2_OK;
 }
 
@@ -1129,7 +1130,7 @@ extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
 extern "C" int b2_op_rmsnorm(const float* x, const float* g, void* ob, float* of, int M, int H, float eps, void* stream) {
   CKR(require_gpu(0));
   if (H % 128 || H > 128 * NORM_MAXV) return fail(B2_ERR_ARG, "H=%d must be a multiple of 128 and <= %d", H, 128 * NORM_MAXV);
-  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(const_cast<float*>(x), g, static_cast<bf16*>(ob), H, 0, of, M, H, eps, nullptr, 0, 0);
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, static_cast<bf16*>(ob), H, 0, of, M, H, eps);
   CK(cudaGetLastError());
   return B2_OK;
 }
