@@ -110,14 +110,6 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
     if (MASK) x = static_cast<unsigned>(rel + i) < span ? x : -INFINITY;
     e[i] = fast_exp2(x);
   }
-  // fp32 -> bf16 by TRUNCATION (keep the high 16 bits; one PRMT per pair) instead of cvt.rn: the convert
-  // instruction shares the quarter-rate XU pipe with MUFU.EX2, which is the bottleneck of this loop.  The row sum
-  // is taken over the truncated values, so numerator and denominator of the softmax carry the same (downward)
-  // rounding and it cancels in O = sum(P.V) / sum(P).  The precise mode keeps round-to-nearest (it stores P_lo).
-  if (!sPlo) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) e[i] = __uint_as_float(__float_as_uint(e[i]) & 0xFFFF0000u);
-  }
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     sum[0] += e[i];
@@ -129,17 +121,10 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint4 u;
-    if (!sPlo) {
-      u.x = __byte_perm(__float_as_uint(e[8 * i + 0]), __float_as_uint(e[8 * i + 1]), 0x7632);
-      u.y = __byte_perm(__float_as_uint(e[8 * i + 2]), __float_as_uint(e[8 * i + 3]), 0x7632);
-      u.z = __byte_perm(__float_as_uint(e[8 * i + 4]), __float_as_uint(e[8 * i + 5]), 0x7632);
-      u.w = __byte_perm(__float_as_uint(e[8 * i + 6]), __float_as_uint(e[8 * i + 7]), 0x7632);
-    } else {
-      u.x = pack_bf16(e[8 * i + 0], e[8 * i + 1]);
-      u.y = pack_bf16(e[8 * i + 2], e[8 * i + 3]);
-      u.z = pack_bf16(e[8 * i + 4], e[8 * i + 5]);
-      u.w = pack_bf16(e[8 * i + 6], e[8 * i + 7]);
-    }
+    u.x = pack_bf16(e[8 * i + 0], e[8 * i + 1]);
+    u.y = pack_bf16(e[8 * i + 2], e[8 * i + 3]);
+    u.z = pack_bf16(e[8 * i + 4], e[8 * i + 5]);
+    u.w = pack_bf16(e[8 * i + 6], e[8 * i + 7]);
     const int chunk16 = (c & 1) * 4 + i;
     *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
   }
