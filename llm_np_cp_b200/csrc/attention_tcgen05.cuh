@@ -163,8 +163,7 @@ template <int SCH, int OCH>
 __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_row, uint8_t* sP, int r, bool need_mask,
                                                  int lo, unsigned span, bool cap, float sl2, float cap_in, float cap_out,
                                                  float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity,
-                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr, AttTrace* tr = nullptr,
-                                                 uint64_t* xu_wait = nullptr, uint32_t xu_parity = 0, uint64_t* xu_arrive = nullptr) {
+                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr, AttTrace* tr = nullptr) {
   constexpr float TAU = 8.0f;   // lazy-rescale threshold (log2 units): P stays <= 2^8
   uint32_t x[SCH][32];
 #pragma unroll
@@ -211,11 +210,6 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
     }
   }
   const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
-  // XU token: the two q tiles of a CTA take turns in the exponential phase (it saturates the MUFU pipe on its
-  // own; run concurrently both would just take twice as long, run alternately each overlaps the other's TMEM
-  // loads / row max / barrier waits)
-  if (xu_wait) mbar_wait(xu_wait, xu_parity);
-  if (tr) tr->ev(36);
   float lsum;
   if (cap) {
     lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo)
@@ -225,7 +219,6 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
                      : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo);
   }
   l += lsum;
-  if (xu_arrive) mbar_arrive(xu_arrive);
 }
 
 // O / l -> bf16 -> out row (the reference's transpose+reshape, llama3.2_model_numpy.py:509-511)
@@ -545,8 +538,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   uint64_t* s_free = bars + 12;      // [2]  S_g copied to registers by all 128 softmax threads
   uint64_t* p_ready = bars + 14;     // [2]  P_g written to smem by all 128 softmax threads
   uint64_t* o_done = bars + 16;      // [2]  O_g += P_g.V finished
-  uint64_t* xu_tok = bars + 18;      // [2]  exponential-phase token of q tile g (arrivals from the other tile)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
@@ -570,7 +562,6 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       mbar_init(&s_free[g], 128);
       mbar_init(&p_ready[g], 128);
       mbar_init(&o_done[g], 1);
-      mbar_init(&xu_tok[g], 128);
     }
     fence_barrier_init();
   }
@@ -714,10 +705,6 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const int n_tiles = je[g] - jb[g];
     AttTrace tr;
     tr.init(((warp & 3) == 0 && lane == 0) ? p.trace : nullptr, 1 + g);
-    // XU token (mbarriers xu_tok[g], 128 arrivals each): strict alternation of the exponential phases --
-    //   q tile 0 starts exp(it)  once q tile 1 has finished exp(it-1)   (it >= 1, while tile 1 still has tiles)
-    //   q tile 1 starts exp(it)  once q tile 0 has finished exp(it)     (while tile 0 still has tiles)
-    const int n_other = je[1 - g] - jb[1 - g];
     for (int it = 0; it < n_tiles; ++it) {
       const int kv0 = (jb[g] + it) * BNKV;
       const bool need_mask = (p.causal && kv0 + BNKV - 1 > t0 + q0) || (kv0 + BNKV > T) ||
@@ -735,9 +722,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       tr.ev(31);
       tc_fence_after();
       att_softmax_tile<SCH, OCH>(tS_row, tO_row, sPg, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l, it > 0,
-                                 &o_done[g], (it - 1) & 1, &s_free[g], nullptr, &tr,
-                                 (g == 0 ? (it >= 1 && it - 1 < n_other) : (it < n_other)) ? &xu_tok[g] : nullptr,
-                                 g == 0 ? ((it - 1) & 1) : (it & 1), &xu_tok[1 - g]);
+                                 &o_done[g], (it - 1) & 1, &s_free[g], nullptr, &tr);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[g]);

@@ -221,7 +221,7 @@ def stage_attn_trace():
     t00 = min(int(t[r, 0, 1]) for r in range(4) if t[r, 0, 1] > 0)
     names = {0: "mma:start", 1: "mma:q_ready", 10: "mma:sfree0", 11: "mma:sfree1", 12: "mma:k_next0", 13: "mma:k_next1", 20: "mma:pready0",
              21: "mma:pready1", 22: "mma:pv0_issued", 23: "mma:pv1_issued", 30: "sm:wait_s", 31: "sm:s_full", 32: "sm:s_in_regs",
-             33: "sm:max_done", 34: "sm:o_done", 35: "sm:p_written", 36: "sm:xu_token"}
+             33: "sm:max_done", 34: "sm:o_done", 35: "sm:p_written"}
     for r, nm in enumerate(["MMA g0", "SOFTMAX g0", "SOFTMAX g1", "MMA g1"]):
         ev = [(int(a), int(c) - t00) for a, c in t[r] if c > 0]
         print(f"--- {nm}: {len(ev)} events, span {ev[-1][1] if ev else 0} cycles")
@@ -240,8 +240,7 @@ def stage_attn_trace():
                 if a == 32 and 31 in last: d["ld S -> regs"].append(c - last[31])
                 if a == 33 and 32 in last: d["row max"].append(c - last[32])
                 if a == 34 and 33 in last: d["wait o_done"].append(c - last[33])
-                if a == 36: d["wait xu token"].append(c - last.get(34, last.get(33, c)))
-                if a == 35: d["exp+P write"].append(c - last.get(36, c))
+                if a == 35: d["exp+P write"].append(c - last.get(34, last.get(33, c)))
             for k2, v in d.items():
                 print(f"   [{nm}] {k2:14s} mean {np.mean(v):8.1f}  max {max(v):6d}  n={len(v)}")
 
