@@ -486,14 +486,14 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 //   warps 0-3   softmax / correction / epilogue of q tile 0        (thread = q row = TMEM lane)
 //   warps 4-7   same for q tile 1
 //   warp  8     TMA producer: both Q tiles once, K/V tiles through a 3-stage ring (shared by both q tiles)
-//   warps 9,10  tcgen05.mma issuers, one per q tile (warp 11 idle; it only completes the third warpgroup)
+//   warp  9     tcgen05.mma issuer (warps 10-11 idle; they only complete the third warpgroup)
 // Register budget is moved with setmaxnreg: the softmax warpgroups hold a whole S row (128 fp32) in registers
 // so TMEM is read once per score; the producer/MMA warpgroup gives its registers away.
-// Per kv tile j the issuer of q tile g does:
-//     wait S_g(j) consumed  -> S_g(j+1) = Q_g.K_(j+1)^T
-//     wait P_g(j) written   -> O_g     += P_g(j).V_j
-// so the next scores are already in TMEM when the q tile's softmax warps finish the current ones, and the two
-// q tiles never wait for each other (only the K/V ring slots are shared: released after both have read them).
+// Per kv tile j and q tile g the MMA warp issues, in this order:
+//     wait S_g(j) consumed  -> S_g(j+1) = Q_g.K_(j+1)^T        (for g = 0, 1)
+//     wait P_g(j) written   -> O_g     += P_g(j).V_j           (for g = 0, 1)
+// so the next scores are already in TMEM when a q tile's softmax warps finish the current ones, and P.V of
+// one q tile overlaps the exponentials of the other.
 // TMEM: S0 | S1 | O0 | O1  (2*BNKV + 2*HD <= 512 columns).
 // ---------------------------------------------------------------------------------------------
 constexpr int ATT2_THREADS = 384;
@@ -555,7 +555,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     for (int s = 0; s < ST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 2);       // one arrival per MMA issuer (= per q tile)
+      mbar_init(&kv_empty[s], 1);
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
@@ -626,63 +626,90 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           }
         }
       }
-    } else if (warp == 9 || warp == 10) {
-      // ------------------------------ MMA issuers: one per q tile, fully independent ------------------------------
-      // Each issuer only follows its own q tile:  S(j+1) as soon as S(j) has been copied to registers,
-      // P.V(j) as soon as P(j) is in smem.  Neither q tile can hold the other one up, so their softmax phases drift
-      // apart and the MUFU-heavy part of one overlaps the TMEM loads / row max of the other.
+    } else if (warp == 9) {
+      // ------------------------------ MMA issuer ------------------------------
       if (elect_one()) {
-        const int g = warp - 9;
         constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
         constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // P (K-major) x V (MN-major)
-        const uint32_t q_addr = smem_u32(sQ + g * Cfg::Q_BYTES);
-        const uint32_t p_addr = smem_u32(sP + g * Cfg::P_BYTES);
-        const uint32_t tSg = tmem_base + g * BNKV, tOg = tmem_base + 2 * BNKV + g * HD;
-        auto st_of = [&](int j) { return (j - j_lo) % ST; };
-        auto ph_of = [&](int j) { return static_cast<uint32_t>(((j - j_lo) / ST) & 1); };
-        auto issue_s = [&](int j) {    // S_g = Q_g . K_j^T
-          mbar_wait(&k_full[st_of(j)], ph_of(j));
-          tc_fence_after();
-          const uint32_t k_addr = smem_u32(sK + st_of(j) * Cfg::KV_BYTES);
+        auto issue_s = [&](int g, int stage) {    // S_g = Q_g . K^T
+          const uint32_t q_addr = smem_u32(sQ + g * Cfg::Q_BYTES);
+          const uint32_t k_addr = smem_u32(sK + stage * Cfg::KV_BYTES);
 #pragma unroll
           for (int hb = 0; hb < HB; ++hb)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tSg, umma_smem_desc(q_addr + hb * (ATT_BM * 128) + k * 32, 16, 1024),
+              umma_bf16_ss(tmem_base + g * BNKV, umma_smem_desc(q_addr + hb * (ATT_BM * 128) + k * 32, 16, 1024),
                            umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024), idesc_s, (hb | k) != 0 ? 1u : 0u);
           umma_commit(&s_full[g]);
         };
-        AttTrace tr;
-        tr.init(p.trace, g == 0 ? 0 : 3);
-        mbar_wait(bar_q, 0);
-        for (int j = j_lo; j < j_hi; ++j) {
-          if (j < jb[g] || j >= je[g]) {
-            // this q tile does not read kv tile j: release the ring slot once the tile has landed (ordering: the
-            // slot's previous tenant has then been released by both issuers)
-            mbar_wait(&k_full[st_of(j)], ph_of(j));
-            umma_commit(&kv_empty[st_of(j)]);
-            continue;
-          }
-          const int it = j - jb[g];
-          if (it == 0) issue_s(j);
-          if (j + 1 < je[g]) {
-            mbar_wait(&s_free[g], it & 1);          // S_g(j) is in registers
-            tr.ev(10);
-            issue_s(j + 1);
-            tr.ev(12);
-          }
-          mbar_wait(&p_ready[g], it & 1);           // P_g(j) is in smem
-          tr.ev(20);
-          mbar_wait(&v_full[st_of(j)], ph_of(j));
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(sV + st_of(j) * Cfg::KV_BYTES);
+        auto issue_pv = [&](int g, int stage, bool first) {   // O_g (+)= P_g . V
+          const uint32_t p_addr = smem_u32(sP + g * Cfg::P_BYTES);
+          const uint32_t v_addr = smem_u32(sV + stage * Cfg::KV_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BNKV / 16; ++kk)
-            umma_bf16_ss(tOg, umma_smem_desc(p_addr + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
-                         umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (it | kk) != 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_base + 2 * BNKV + g * HD,
+                         umma_smem_desc(p_addr + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
+                         umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (!first || kk != 0) ? 1u : 0u);
           umma_commit(&o_done[g]);
-          umma_commit(&kv_empty[st_of(j)]);
-          tr.ev(22);
+        };
+        AttTrace tr;
+        tr.init(p.trace, 0);
+        tr.ev(0);
+        mbar_wait(bar_q, 0);
+        tr.ev(1);
+        auto has = [&](int g, int j) { return j >= jb[g] && j < je[g]; };
+        auto st_of = [&](int j) { return (j - j_lo) % ST; };
+        auto ph_of = [&](int j) { return static_cast<uint32_t>(((j - j_lo) / ST) & 1); };
+        if (j_lo < j_hi) {
+          mbar_wait(&k_full[0], 0);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            if (has(g, j_lo)) issue_s(g, 0);
+        }
+        // Skewed schedule: q tile 1 runs half an iteration behind q tile 0, so the exponentials (MUFU) of one tile
+        // overlap the TMEM loads / row max / waits of the other instead of both fighting for the XU pipe at once.
+        //   per kv tile j:  S0(j+1) | PV1(j-1) | S1(j+1) | PV0(j)
+        for (int j = j_lo; j <= j_hi; ++j) {
+          // (1) q tile 0: next scores as soon as the current ones are in registers
+          if (has(0, j + 1)) {
+            if (has(0, j)) mbar_wait(&s_free[0], (j - jb[0]) & 1);
+            tr.ev(10);
+            mbar_wait(&k_full[st_of(j + 1)], ph_of(j + 1));
+            tr.ev(12);
+            tc_fence_after();
+            issue_s(0, st_of(j + 1));
+          }
+          // (2) q tile 1: P.V of the previous kv tile; it is the last reader of that ring slot
+          if (j > j_lo && has(1, j - 1)) {
+            mbar_wait(&p_ready[1], (j - 1 - jb[1]) & 1);
+            tr.ev(21);
+            mbar_wait(&v_full[st_of(j - 1)], ph_of(j - 1));
+            tc_fence_after();
+            issue_pv(1, st_of(j - 1), j - 1 == jb[1]);
+            tr.ev(23);
+            umma_commit(&kv_empty[st_of(j - 1)]);
+          }
+          if (j == j_hi) break;
+          // (3) q tile 1: next scores
+          if (has(1, j + 1)) {
+            if (has(1, j)) mbar_wait(&s_free[1], (j - jb[1]) & 1);
+            tr.ev(11);
+            mbar_wait(&k_full[st_of(j + 1)], ph_of(j + 1));
+            tr.ev(13);
+            tc_fence_after();
+            issue_s(1, st_of(j + 1));
+          }
+          // (4) q tile 0: P.V of this kv tile
+          if (has(0, j)) {
+            mbar_wait(&p_ready[0], (j - jb[0]) & 1);
+            tr.ev(20);
+            mbar_wait(&v_full[st_of(j)], ph_of(j));
+            tc_fence_after();
+            issue_pv(0, st_of(j), j == jb[0]);
+            tr.ev(22);
+            if (!has(1, j)) umma_commit(&kv_empty[st_of(j)]);   // q tile 1 does not read this kv tile
+          }
         }
       }
     }

@@ -210,26 +210,26 @@ def stage_attn_trace():
     q = bf16_randn(B * S, NH * HD, seed=13)
     kc, vc = bf16_randn(B, NKV, S, HD, seed=14), bf16_randn(B, NKV, S, HD, seed=15)
     out = torch.zeros((B * S, NH * HD), dtype=torch.bfloat16, device="cuda")
-    trace = torch.zeros(4 * 1024, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(3 * 1024, dtype=torch.int64, device="cuda")
     os.environ["B2_ATT_TRACE"] = hex(trace.data_ptr())
     for _ in range(2):
         trace.zero_()
         _lib.check(L().b2_op_attention(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), out.data_ptr(), B, S, NH, NKV, HD, S, 0,
                                        float(1 / math.sqrt(HD)), 0.0, 1, 0, 0, stream()))
         torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(4, 512, 2)
-    t00 = min(int(t[r, 0, 1]) for r in range(4) if t[r, 0, 1] > 0)
+    t = trace.cpu().numpy().reshape(3, 512, 2)
+    t00 = min(int(t[r, 0, 1]) for r in range(3) if t[r, 0, 1] > 0)
     names = {0: "mma:start", 1: "mma:q_ready", 10: "mma:sfree0", 11: "mma:sfree1", 12: "mma:k_next0", 13: "mma:k_next1", 20: "mma:pready0",
              21: "mma:pready1", 22: "mma:pv0_issued", 23: "mma:pv1_issued", 30: "sm:wait_s", 31: "sm:s_full", 32: "sm:s_in_regs",
              33: "sm:max_done", 34: "sm:o_done", 35: "sm:p_written"}
-    for r, nm in enumerate(["MMA g0", "SOFTMAX g0", "SOFTMAX g1", "MMA g1"]):
+    for r, nm in enumerate(["MMA", "SOFTMAX g0", "SOFTMAX g1"]):
         ev = [(int(a), int(c) - t00) for a, c in t[r] if c > 0]
         print(f"--- {nm}: {len(ev)} events, span {ev[-1][1] if ev else 0} cycles")
         prev = 0
-        for k, (a, c) in enumerate(ev[:40] if r in (0, 3) else ev[:30]):
+        for k, (a, c) in enumerate(ev[:70] if r == 0 else ev[:44]):
             print(f"   {c:8d} (+{c - prev:6d}) {names.get(a, a)}")
             prev = c
-        if r in (1, 2) and ev:
+        if r > 0 and ev:
             # per-tile summary over all tiles
             import collections
             d = collections.defaultdict(list)
