@@ -52,6 +52,9 @@ struct AttTrace {
   }
 };
 
+#ifndef ATT_POLY
+#define ATT_POLY 2
+#endif
 constexpr int ATT_BM = 128;
 constexpr int ATT_THREADS = 192;
 
