@@ -53,7 +53,7 @@ struct AttTrace {
 };
 
 #ifndef ATT_POLY
-#define ATT_POLY 2
+#define ATT_POLY 0
 #endif
 constexpr int ATT_BM = 128;
 constexpr int ATT_THREADS = 192;
