@@ -331,6 +331,11 @@ def main():
         gemm_tf = st["gemm_flops"] / (st["gemm_ms"] * 1e-3) / 1e12 if st["gemm_ms"] > 0 else None
         attn_tf = st["attn_flops"] / (st["attn_ms"] * 1e-3) / 1e12 if st["attn_ms"] > 0 else None
         peak = pk["tf_sustained"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if a.model == "1b" and S == 2048 and B == 8 and os.path.exists(tpath):   # the ncu capture is for exactly this workload
+            with open(tpath) as f:
+                traffic = json.load(f)["avg_dram_bytes_per_gemm_launch"]
         line = {
             "metric": "prefill_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -345,7 +350,8 @@ def main():
             "model_frac_of_peak": value / world * f_tok / 1e12 / peak,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all fused-epilogue variants)",
                          "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": None,
+                         "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": traffic,
+                         "traffic_note": "avg DRAM bytes per GEMM launch from profiles/r01_gemm_traffic.json (ncu --set full); algorithmic 507 MB",
                          "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                          "gemm_ms_per_step": st["gemm_ms"] / a.steps, "gemm_share_of_step": st["gemm_ms"] / ms,
                          "attention": {"achieved": attn_tf, "ms_per_step": st["attn_ms"] / a.steps,

@@ -25,7 +25,7 @@ for i, r in enumerate(rows):
 ia, ie, isamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 c, s = Counter(), Counter()
 for r in data:
-    if len(r) <= ie: continue
+    if len(r) <= ie or not (r[ie] or '0').replace('.','').isdigit(): continue
     t = r[ia].split()
     op = t[1] if t[0].startswith("@") else t[0]
     c[op] += int(r[ie] or 0); s[op] += int(r[isamp] or 0)
