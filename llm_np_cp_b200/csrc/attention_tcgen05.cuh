@@ -157,10 +157,12 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
 // S lives at tS_row, O at tO_row (TMEM, this thread's lane), P goes to sP (smem, 128B-swizzled rows).
 template <int SCH, bool MASK, bool CAP>
 __device__ __forceinline__ float att_exp_regs(uint32_t (&x)[SCH][32], uint8_t* sP, int r, float sl2, float m_safe,
-                                              float cap_in, float cap_out, int lo, unsigned span, uint8_t* sPlo) {
+                                              float cap_in, float cap_out, int lo, unsigned span, uint8_t* sPlo,
+                                              int c_off = 0) {
   float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < SCH; ++c) att_exp32<MASK, CAP>(x[c], c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum, sPlo);
+  for (int c = 0; c < SCH; ++c)
+    att_exp32<MASK, CAP>(x[c], c_off + c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum, sPlo);
   return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
@@ -168,7 +170,12 @@ template <int SCH, int OCH>
 __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_row, uint8_t* sP, int r, bool need_mask,
                                                  int lo, unsigned span, bool cap, float sl2, float cap_in, float cap_out,
                                                  float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity,
-                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr, AttTrace* tr = nullptr) {
+                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr, AttTrace* tr = nullptr,
+                                                 int c_off = 0, float* mx_mine = nullptr, const float* mx_other = nullptr,
+                                                 int pair_bar = 0) {
+  // c_off / mx_* / pair_bar: split-row mode -- this thread owns only chunks [c_off, c_off + SCH) of the row (tS_row,
+  // tO_row already point at its columns); the row max is exchanged with the partner thread (other warp, same TMEM
+  // lanes) through shared memory + a 64-thread named barrier so both use the same scale.
   constexpr float TAU = 8.0f;   // lazy-rescale threshold (log2 units): P stays <= 2^8
   uint32_t x[SCH][32];
 #pragma unroll
@@ -182,12 +189,17 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
   float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   if (need_mask) {
 #pragma unroll
-    for (int c = 0; c < SCH; ++c) att_max32<true>(x[c], c * 32 - lo, span, m);
+    for (int c = 0; c < SCH; ++c) att_max32<true>(x[c], (c_off + c) * 32 - lo, span, m);
   } else {
 #pragma unroll
     for (int c = 0; c < SCH; ++c) att_max32<false>(x[c], 0, 0u, m);
   }
-  const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+  float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+  if (mx_mine) {
+    *mx_mine = mx;
+    named_bar_sync(pair_bar, 64);
+    mx = fmaxf(mx, *mx_other);
+  }
   float m_tile = mx;                               // -> log2 domain, after the optional soft-cap
   if (mx != -INFINITY) m_tile = cap ? cap_out * fast_tanh(mx * cap_in) : mx * sl2;
   float alpha = 1.0f;
@@ -217,11 +229,11 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
   const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
   float lsum;
   if (cap) {
-    lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo)
-                     : att_exp_regs<SCH, false, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo);
+    lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off)
+                     : att_exp_regs<SCH, false, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off);
   } else {
-    lsum = need_mask ? att_exp_regs<SCH, true, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo)
-                     : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo);
+    lsum = need_mask ? att_exp_regs<SCH, true, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off)
+                     : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off);
   }
   l += lsum;
 }
@@ -501,7 +513,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // one q tile overlaps the exponentials of the other.
 // TMEM: S0 | S1 | O0 | O1  (2*BNKV + 2*HD <= 512 columns).
 // ---------------------------------------------------------------------------------------------
-constexpr int ATT2_THREADS = 384;
+// SPLIT = softmax threads per q row: 1 (8 softmax warps, whole row in registers) or 2 (16 softmax warps, each thread
+// owns half of the kv columns of its row and half of the O columns; 4 warps per scheduler hide the in-order MUFU /
+// dependency stalls of the exponential phase)
+template <int SPLIT>
+constexpr int att2_threads() { return 32 * (8 * SPLIT + 4); }
 
 
 template <int HD>
@@ -512,13 +528,14 @@ struct Attn2Cfg {
   static constexpr int KV_BYTES = BNKV * HD * 2;         // one K or V tile
   static constexpr int P_BYTES = ATT_BM * BNKV * 2;      // one P tile
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + BAR_BYTES + 1024;
+  static constexpr int EX_BYTES = 8192;                  // row-max / row-sum exchange between the two threads of a row
+  static constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + BAR_BYTES + EX_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
   static_assert(2 * BNKV + 2 * HD <= 512, "TMEM budget");
 };
 
-template <int HD>
-__global__ void __launch_bounds__(ATT2_THREADS, 1)
+template <int HD, int SPLIT>
+__global__ void __launch_bounds__(att2_threads<SPLIT>(), 1)
 attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = Attn2Cfg<HD>;
@@ -527,6 +544,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   constexpr int HB = HD / 64;
   constexpr int SCH = BNKV / 32;
   constexpr int OCH = HD / 32;
+  constexpr int SMW = 8 * SPLIT;                       // softmax warps; warp SMW = TMA producer, SMW + 1 = MMA issuer
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -544,6 +562,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   uint64_t* p_ready = bars + 14;     // [2]  P_g written to smem by all 128 softmax threads
   uint64_t* o_done = bars + 16;      // [2]  O_g += P_g.V finished
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* ex = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [2 g][128 rows][2 halves][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
@@ -552,7 +571,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / (p.NH / p.NKV);
 
-  if (warp == 8 && lane == 0) {
+  if (warp == SMW && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
@@ -564,13 +583,13 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_free[g], 128);
-      mbar_init(&p_ready[g], 128);
+      mbar_init(&s_free[g], 128 * SPLIT);
+      mbar_init(&p_ready[g], 128 * SPLIT);
       mbar_init(&o_done[g], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == SMW + 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
@@ -598,9 +617,9 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int j_lo = (je[1] > jb[1]) ? min(jb[0], jb[1]) : jb[0];
   const int j_hi = max(je[0], je[1]);
 
-  if (warp >= 8) {
+  if (warp >= SMW) {
     setmaxnreg_dec<40>();
-    if (warp == 8) {
+    if (warp == SMW) {
       // ------------------------------ TMA producer ------------------------------
       if (elect_one()) {
         mbar_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
@@ -631,7 +650,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           }
         }
       }
-    } else if (warp == 9) {
+    } else if (warp == SMW + 1) {
       // ------------------------------ MMA issuer ------------------------------
       if (elect_one()) {
         constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
@@ -720,13 +739,18 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
   } else {
     // ------------------------------ softmax / correction / epilogue (8 warps, 2 q tiles) ------------------------------
-    setmaxnreg_inc<232>();
-    const int g = warp >> 2;                         // q tile of this warp
-    const int r = (warp & 3) * 32 + lane;            // row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS_row = tmem_base + g * BNKV + lane_off;
-    const uint32_t tO_row = tmem_base + 2 * BNKV + g * HD + lane_off;
+    setmaxnreg_inc<(SPLIT == 1) ? 232 : 104>();
+    const int g = (warp >> 2) & 1;                   // q tile of this warp
+    const int half = warp >> 3;                      // which half of the row's columns (SPLIT == 2), else 0
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;               // row inside the tile == TMEM lane
+    constexpr int SCHL = SCH / SPLIT, OCHL = OCH / SPLIT;   // chunks of S / of O owned by this thread
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS_row = tmem_base + g * BNKV + half * (SCHL * 32) + lane_off;
+    const uint32_t tO_row = tmem_base + 2 * BNKV + g * HD + half * (OCHL * 32) + lane_off;
     uint8_t* sPg = sP + g * Cfg::P_BYTES;
+    float* exr = ex + ((g * 128 + r) * 2) * 4;       // this row's exchange slots: [half][0,1 = max by tile parity, 2 = l]
+    const int pair_bar = 1 + g * 4 + quarter;        // named barrier shared by the two warps of this (q tile, quarter)
     const int q0 = q0g[g];
     const int qpos = t0 + q0 + r;
     const float LOG2E = 1.4426950408889634f;
@@ -736,7 +760,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     float m_used = -INFINITY, l = 0.f;
     const int n_tiles = je[g] - jb[g];
     AttTrace tr;
-    tr.init(((warp & 3) == 0 && lane == 0) ? p.trace : nullptr, 1 + g);
+    tr.init((quarter == 0 && half == 0 && lane == 0) ? p.trace : nullptr, 1 + g);
     for (int it = 0; it < n_tiles; ++it) {
       const int kv0 = (jb[g] + it) * BNKV;
       const bool need_mask = (p.causal && kv0 + BNKV - 1 > t0 + q0) || (kv0 + BNKV > T) ||
@@ -753,8 +777,9 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       mbar_wait(&s_full[g], it & 1);
       tr.ev(31);
       tc_fence_after();
-      att_softmax_tile<SCH, OCH>(tS_row, tO_row, sPg, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l, it > 0,
-                                 &o_done[g], (it - 1) & 1, &s_free[g], nullptr, &tr);
+      att_softmax_tile<SCHL, OCHL>(tS_row, tO_row, sPg, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l, it > 0,
+                                   &o_done[g], (it - 1) & 1, &s_free[g], nullptr, &tr, half * SCHL,
+                                   SPLIT == 2 ? exr + half * 4 + (it & 1) : nullptr, exr + (1 - half) * 4 + (it & 1), pair_bar);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[g]);
@@ -764,12 +789,18 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       mbar_wait(&o_done[g], (n_tiles - 1) & 1);
       tc_fence_after();
     }
+    if (SPLIT == 2) {                                // row sum = sum of the two halves (same scale m_used in both)
+      exr[half * 4 + 2] = l;
+      named_bar_sync(pair_bar, 64);
+      l += exr[(1 - half) * 4 + 2];
+    }
     if (2 * pi + g < n_qt)
-      att_store_out<OCH>(tO_row, n_tiles > 0, l, (q0 + r) < p.S, p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD);
+      att_store_out<OCHL>(tO_row, n_tiles > 0, l, (q0 + r) < p.S,
+                          p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD + half * (OCHL * 32));
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == SMW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -228,10 +228,10 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return B2_OK;
 }
 
-template <int HD>
+template <int HD, int SPLIT>
 static int launch_attn_pair_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                               cudaStream_t st) {
-  auto kern = attn_prefill_pair_kernel<HD>;
+  auto kern = attn_prefill_pair_kernel<HD, SPLIT>;
   static bool attr[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -241,7 +241,7 @@ static int launch_attn_pair_t(const CUtensorMap& tq, const CUtensorMap& tk, cons
   }
   const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
   dim3 grid((n_qt + 1) / 2, p.NH, p.B);
-  CK(launch_k(kern, grid, dim3(ATT2_THREADS), Attn2Cfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
+  CK(launch_k(kern, grid, dim3(att2_threads<SPLIT>()), Attn2Cfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
   return B2_OK;
 }
 
@@ -268,7 +268,11 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
     if (HD == 128) return launch_attn_t<128, 2>(tq, tk, tv, p, st);
     return fail(B2_ERR_ARG, "precise mode supports head_dim 64 and 128 only");
   }
-  if (pair) return HD == 64 ? launch_attn_pair_t<64>(tq, tk, tv, p, st) : launch_attn_pair_t<128>(tq, tk, tv, p, st);
+  if (pair) {
+    static const int split = getenv("B2_ATTN_SPLIT") ? atoi(getenv("B2_ATTN_SPLIT")) : 2;   // softmax threads per q row
+    if (split == 2) return HD == 64 ? launch_attn_pair_t<64, 2>(tq, tk, tv, p, st) : launch_attn_pair_t<128, 2>(tq, tk, tv, p, st);
+    return HD == 64 ? launch_attn_pair_t<64, 1>(tq, tk, tv, p, st) : launch_attn_pair_t<128, 1>(tq, tk, tv, p, st);
+  }
   if (HD == 64) return launch_attn_t<64, 1>(tq, tk, tv, p, st);
   if (HD == 128) return launch_attn_t<128, 1>(tq, tk, tv, p, st);
   if (HD == 256) return launch_attn_t<256, 1>(tq, tk, tv, p, st);
