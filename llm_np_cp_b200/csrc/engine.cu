@@ -269,7 +269,7 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
     return fail(B2_ERR_ARG, "precise mode supports head_dim 64 and 128 only");
   }
   if (pair) {
-    static const int split = getenv("B2_ATTN_SPLIT") ? atoi(getenv("B2_ATTN_SPLIT")) : 2;   // softmax threads per q row
+    static const int split = getenv("B2_ATTN_SPLIT") ? atoi(getenv("B2_ATTN_SPLIT")) : 1;   // softmax threads per q row (2 measured slower: the XU pipe, not latency, bounds the exp phase)
     if (split == 2) return HD == 64 ? launch_attn_pair_t<64, 2>(tq, tk, tv, p, st) : launch_attn_pair_t<128, 2>(tq, tk, tv, p, st);
     return HD == 64 ? launch_attn_pair_t<64, 1>(tq, tk, tv, p, st) : launch_attn_pair_t<128, 1>(tq, tk, tv, p, st);
   }
@@ -829,7 +829,9 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
       p.t0_ptr = cache->t0_dev;
       p.rope_cos = e->rope_cos;
       p.rope_sin = e->rope_sin;
-      CKR(eng_gemm(e, st, pick_bn(M, p.N, HD), EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
+      static const int qkv_bn = getenv("B2_QKV_BN") ? atoi(getenv("B2_QKV_BN")) : 0;   // bring-up knob
+      const int bn_qkv = (qkv_bn >= HD && M > 128) ? qkv_bn : pick_bn(M, p.N, HD);
+      CKR(eng_gemm(e, st, bn_qkv, EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
     }
     const int window = (c.sliding_window > 0 && (li % 2 == 0)) ? c.sliding_window : 0;
     if (decode) {

@@ -188,6 +188,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
     const float* cosr = p.rope_cos + static_cast<size_t>(pos) * (HD >> 1);
     const float* sinr = p.rope_sin + static_cast<size_t>(pos) * (HD >> 1);
     // work items: (head hh, half-chunk i); this warp takes the items of its parity
+    float4 cs4[8], sn4[8];   // cos/sin of this row's position for half-chunk tab_i (reused across the heads of a tile)
+    int tab_i = -1;
 #pragma unroll 1
     for (int t = half; t < BN / 64; t += 2) {
       const int hh = t / half_chunks, i = t - hh * half_chunks;
@@ -216,8 +218,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
       const int cl = hh * (HD >> 5) + i;  // chunk holding x1 (first half of the head)
       tmem_ld32(trow + cl * 32, a);
       tmem_ld32(trow + (cl + half_chunks) * 32, c);  // matching x2 chunk (second half)
-      float4 cs4[8], sn4[8];
-      if (rope && row_ok) {   // table loads overlap the TMEM load latency
+      if (rope && row_ok && i != tab_i) {   // table loads overlap the TMEM load latency; head_dim 64: one load per tile
         const float4* c4 = reinterpret_cast<const float4*>(cosr + i * 32);
         const float4* s4 = reinterpret_cast<const float4*>(sinr + i * 32);
 #pragma unroll
@@ -225,6 +226,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
           cs4[j] = __ldg(c4 + j);
           sn4[j] = __ldg(s4 + j);
         }
+        tab_i = i;
       }
       __syncwarp();
       tmem_ld_wait();
