@@ -15,6 +15,7 @@
 #include "attention_tcgen05.cuh"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 
 using namespace b2;
 typedef __nv_bfloat16 bf16;
@@ -180,6 +181,35 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 }
 
 // tc: fp32 output map ({32 x 32} boxes) for EPI_F32 / EPI_RESID; any valid map otherwise (unused)
+// 2-CTA (cta_group::2) variant: 256 x 256 tiles per CTA pair; tb must have {64 x 128} boxes (each CTA loads half of W)
+template <int EPI>
+static int launch_gemm2_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmParams p, cudaStream_t st) {
+  auto kern = gemm2_bf16_kernel<EPI>;
+  static bool attr[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || !attr[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    if (dev < 16) attr[dev] = true;
+  }
+  p.band_m = p.band_m > 1 ? p.band_m / 2 : 1;          // bands are counted in 256-row tiles here
+  const int total = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  int clusters = num_sms() / 2;
+  if (total < clusters) clusters = total;
+  CK(launch_k(kern, dim3(2 * clusters), dim3(GEMM_THREADS), Gemm2Cfg::SMEM_BYTES, st, ta, tb, tc, p));
+  return B2_OK;
+}
+static int launch_gemm2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                        cudaStream_t st) {
+  if (p.split_k != 1) return fail(B2_ERR_ARG, "2-CTA GEMM has no split-K");
+  if (epi == EPI_BF16) return launch_gemm2_t<EPI_BF16>(ta, tb, tc, p, st);
+  if (epi == EPI_F32) return launch_gemm2_t<EPI_F32>(ta, tb, tc, p, st);
+  if (epi == EPI_RESID) return launch_gemm2_t<EPI_RESID>(ta, tb, tc, p, st);
+  if (epi == EPI_QKV_ROPE) return launch_gemm2_t<EPI_QKV_ROPE>(ta, tb, tc, p, st);
+  if (epi == EPI_GLU) return launch_gemm2_t<EPI_GLU>(ta, tb, tc, p, st);
+  return fail(B2_ERR_ARG, "bad epilogue %d", epi);
+}
+
 static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                        const GemmParams& p, cudaStream_t st) {
   if (p.K % GEMM_BK != 0 || p.K <= 0) return fail(B2_ERR_ARG, "GEMM K=%d must be a positive multiple of 64", p.K);
@@ -445,12 +475,14 @@ static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* 
   }
   if (!a_rows) a_rows = e->ws_tokens > p.M ? e->ws_tokens : p.M;
   CKR(get_tmap(e, a, a_rows, p.K, lda, GEMM_BM, &ta));
-  CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, bn, &tb));
+  static const bool use2 = getenv("B2_GEMM2") != nullptr;
+  const bool two_cta = use2 && bn == 256 && p.split_k == 1 && p.N % 256 == 0;
+  CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, two_cta ? 128 : bn, &tb));
   tc = ta;
   if (epi == EPI_F32 || epi == EPI_RESID) CKR(get_tmap(e, p.out, c_rows ? c_rows : p.M, p.N, p.ldo, 32, &tc, true));
   p.band_m = pick_band(p.N, p.k_wrap);
   time_begin(e, st, 2.0 * p.M * static_cast<double>(p.N) * p.K, 0);
-  int r = launch_gemm(bn, epi, *ta, *tb, *tc, p, st);
+  int r = two_cta ? launch_gemm2(epi, *ta, *tb, *tc, p, st) : launch_gemm(bn, epi, *ta, *tb, *tc, p, st);
   time_end(e, st);
   e->st.launches++;
   e->st.gemm_launches++;
@@ -1155,8 +1187,9 @@ extern "C" int b2_op_gemm(const void* a, const void* w, void* out, int M, int N,
   CKR(require_gpu(dev));
   if (epi == EPI_QKV_ROPE) return fail(B2_ERR_ARG, "use b2_op_qkv_rope");
   CUtensorMap ta, tb;
+  const bool two_cta = bn == 512;                     // test hook: bn = 512 selects the 2-CTA kernel (256-wide tiles)
   CKR(make_tmap(&ta, a, M, K, K, GEMM_BM));
-  CKR(make_tmap(&tb, w, N, K, K, bn));
+  CKR(make_tmap(&tb, w, N, K, K, two_cta ? 128 : bn));
   GemmParams p = base_params(M, N, K);
   p.split_k = split_k < 1 ? 1 : split_k;
   p.out = out;
@@ -1166,6 +1199,7 @@ extern "C" int b2_op_gemm(const void* a, const void* w, void* out, int M, int N,
   p.band_m = pick_band(N, K);
   CUtensorMap tc = ta;
   if (epi == EPI_F32 || epi == EPI_RESID) CKR(make_tmap_t(&tc, out, M, N, N, 32, true));
+  if (two_cta) return launch_gemm2(epi, ta, tb, tc, p, static_cast<cudaStream_t>(stream));
   return launch_gemm(bn, epi, ta, tb, tc, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -147,3 +147,27 @@ def test_attention_decode(B, NH, NKV, HD, t0, window, softcap):
     out = op_attention(q, kc, vc, B, 1, NH, NKV, HD, Tmax, t0, scale, softcap, 0, window, decode=1)
     ref = ref_attention(q, kc, vc, B, 1, NH, NKV, HD, t0, scale, softcap, 1, window)
     assert (out.float() - ref).abs().max() <= 1e-2, err_stats(out.float(), ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 512, 256), (1000, 768, 512), (2048, 3072, 2048), (333, 2304, 2304)])
+def test_gemm_2cta_f32(M, N, K):
+    """cta_group::2 kernel (bn=512 selects it): 256 x 256 tiles per CTA pair."""
+    a, w = bf16_randn(M, K, seed=21), bf16_randn(N, K, seed=22)
+    out = op_gemm(a, w, epi=1, bn=512)
+    ref = a.float() @ w.float().T
+    assert (out - ref).abs().max() <= 2e-3 * math.sqrt(K / 64), err_stats(out, ref)
+
+
+def test_gemm_2cta_epilogues():
+    M, I, K = 700, 1024, 512
+    a = bf16_randn(M, K, seed=23)
+    gate, up = bf16_randn(I, K, seed=24, std=0.05), bf16_randn(I, K, seed=25, std=0.05)
+    out = op_gemm(a, interleave_gate_up(gate, up), epi=4, bn=512, act=0)
+    g, u = a.float() @ gate.float().T, a.float() @ up.float().T
+    ref = torch.nn.functional.silu(g) * u
+    assert (out.float() - ref).abs().max() <= ref.abs().max() * 2 ** -7 + 2e-3
+    w = bf16_randn(512, K, seed=26, std=0.05)
+    x0 = torch.randn(M, 512, generator=torch.Generator().manual_seed(7)).to(DEV)
+    x = x0.clone()
+    op_gemm(a, w, epi=2, bn=512, out=x)
+    assert (x - (x0 + a.float() @ w.float().T)).abs().max() < 5e-3

@@ -245,5 +245,27 @@ def stage_attn_trace():
                 print(f"   [{nm}] {k2:14s} mean {np.mean(v):8.1f}  max {max(v):6d}  n={len(v)}")
 
 
+def stage_gemm2():
+    """1-CTA vs 2-CTA GEMM on the model's prefill shapes (event-timed, inputs >> L2 between variants)."""
+    from gpu_util import bf16_randn, op_gemm
+    for (M, N, K, name) in [(16384, 16384, 2048, "gate/up"), (16384, 2048, 8192, "down"), (16384, 3072, 2048, "qkv-shape"), (16384, 2048, 2048, "o_proj")]:
+        a, w = bf16_randn(M, K, seed=1), bf16_randn(N, K, seed=2, std=0.05)
+        out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+        ref = a[:256].float() @ w.float().T
+        for bn in (256, 512):
+            for _ in range(2):
+                op_gemm(a, w, epi=0, bn=bn, out=out)
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            n = 10
+            for _ in range(n):
+                op_gemm(a, w, epi=0, bn=bn, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            err = (out[:256].float() - ref).abs().max().item()
+            print(f"{name:10s} M{M} N{N} K{K} {'2-CTA' if bn == 512 else '1-CTA'}: {ms * 1e3:8.1f} us  {2 * M * N * K / ms / 1e9:7.1f} TFLOP/s  max_err {err:.3g}", flush=True)
+
+
 if __name__ == "__main__":
     globals()["stage_" + sys.argv[1]]()
