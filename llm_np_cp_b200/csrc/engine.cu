@@ -475,7 +475,9 @@ static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* 
   }
   if (!a_rows) a_rows = e->ws_tokens > p.M ? e->ws_tokens : p.M;
   CKR(get_tmap(e, a, a_rows, p.K, lda, GEMM_BM, &ta));
-  static const bool use2 = getenv("B2_GEMM2") != nullptr;
+  // prefill-size GEMMs run on CTA pairs (cta_group::2, 256 x 256 tiles): measured 1420 vs 1300 TFLOP/s in-step for the
+  // 1-CTA kernel (B2_GEMM1=1 selects the latter)
+  static const bool use2 = getenv("B2_GEMM1") == nullptr;
   const bool two_cta = use2 && bn == 256 && p.split_k == 1 && p.N % 256 == 0;
   CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, two_cta ? 128 : bn, &tb));
   tc = ta;
