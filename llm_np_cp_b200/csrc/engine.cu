@@ -812,7 +812,7 @@ static int pick_split(int N, int K, int bn) {
   const int tiles = (N + bn - 1) / bn, kb = K / GEMM_BK;
   int best = 1;
   for (int sp = 2; sp <= MAX_SPLIT; sp *= 2)
-    if (kb % sp == 0 && kb / sp >= 8 && tiles * sp <= 304) best = sp;
+    if (kb % sp == 0 && kb / sp >= 8 && tiles * sp <= 148) best = sp;   // one wave: a second, partial wave costs more than it buys
   return best;
 }
 
@@ -927,7 +927,9 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
       GemmParams p = base_params(M, 2 * I, H);
       p.out = e->hb; p.ldo = pf * I; p.act = c.hidden_act;
       p.lo_off = c.precise ? I : 0;
-      CKR(eng_gemm(e, st, pick_bn(M, 2 * I, 0), EPI_GLU, e->xn, H, Ly.wgu, p));           // act(gate)*up
+      // few rows: 128-wide tiles give exactly one wave of weight-streaming CTAs for the usual 2I / 128 <= 148
+      const int bn_glu = (M <= 128 && (2 * I) / 128 <= 148) ? 128 : pick_bn(M, 2 * I, 0);
+      CKR(eng_gemm(e, st, bn_glu, EPI_GLU, e->xn, H, Ly.wgu, p));                          // act(gate)*up
     }
     if (!c.gemma) {
       GemmParams p = base_params(M, H, I);
