@@ -348,7 +348,7 @@ def main():
             "model_flops_per_token": f_tok,
             "model_tflops_per_gpu": value / world * f_tok / 1e12,
             "model_frac_of_peak": value / world * f_tok / 1e12 / peak,
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all fused-epilogue variants)",
+            "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, all fused-epilogue variants)",
                          "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": traffic,
                          "traffic_note": "avg DRAM bytes per GEMM launch from profiles/r01_gemm_traffic.json (ncu --set full); algorithmic 507 MB",
