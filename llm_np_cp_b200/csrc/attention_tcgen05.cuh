@@ -33,6 +33,7 @@ struct AttnParams {
   int kv_lo_row;         // row offset of the lo plane inside the K/V tensor maps (= B_max*NKV*Tmax)
   int out_lo_col;        // column offset of the lo plane inside an output row
   unsigned long long* trace;   // bring-up: clock64() timeline of CTA (0,0,0); nullptr = off
+  unsigned long long* cta_trace;   // diagnostics: per CTA {globaltimer at start, at end, smid}; nullptr = off
 };
 
 // timeline tracing (diagnostics only): role r of CTA (0,0,0) appends (event id, clock) pairs to trace[r*1024 ...]
@@ -79,20 +80,19 @@ struct AttnCfg {
 // (tcgen05.wait::ld waits for every outstanding load, so it is placed after the compute of chunk c).
 template <bool MASK>
 __device__ __forceinline__ void att_max32(const uint32_t (&sr)[32], int rel, unsigned span, float (&m)[4]) {
+  // FMNMX3 (three-input max): 64 instead of 128 max instructions per 128-score row
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    float v0 = __uint_as_float(sr[i]), v1 = __uint_as_float(sr[i + 1]);
-    float v2 = __uint_as_float(sr[i + 2]), v3 = __uint_as_float(sr[i + 3]);
-    if (MASK) {
-      v0 = static_cast<unsigned>(rel + i) < span ? v0 : -INFINITY;
-      v1 = static_cast<unsigned>(rel + i + 1) < span ? v1 : -INFINITY;
-      v2 = static_cast<unsigned>(rel + i + 2) < span ? v2 : -INFINITY;
-      v3 = static_cast<unsigned>(rel + i + 3) < span ? v3 : -INFINITY;
+  for (int i = 0; i < 32; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = __uint_as_float(sr[i + k]);
+      if (MASK) v[k] = static_cast<unsigned>(rel + i + k) < span ? v[k] : -INFINITY;
     }
-    m[0] = fmaxf(m[0], v0);
-    m[1] = fmaxf(m[1], v1);
-    m[2] = fmaxf(m[2], v2);
-    m[3] = fmaxf(m[3], v3);
+    m[0] = fmax3(m[0], v[0], v[1]);
+    m[1] = fmax3(m[1], v[2], v[3]);
+    m[2] = fmax3(m[2], v[4], v[5]);
+    m[3] = fmax3(m[3], v[6], v[7]);
   }
 }
 
@@ -236,6 +236,7 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
                      : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off);
   }
   l += lsum;
+  if (tr) tr->ev(37);
 }
 
 // O / l -> bf16 -> out row (the reference's transpose+reshape, llama3.2_model_numpy.py:509-511)
@@ -565,6 +566,8 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   float* ex = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [2 g][128 rows][2 halves][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long cta_t0 = 0;
+  if (p.cta_trace && threadIdx.x == 0) cta_t0 = globaltimer_ns();
   const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
   const int n_pairs = (n_qt + 1) / 2;
   const int pi = n_pairs - 1 - static_cast<int>(blockIdx.x);    // heaviest pairs first
@@ -781,6 +784,7 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                                    &o_done[g], (it - 1) & 1, &s_free[g], nullptr, &tr, half * SCHL,
                                    SPLIT == 2 ? exr + half * 4 + (it & 1) : nullptr, exr + (1 - half) * 4 + (it & 1), pair_bar);
       fence_proxy_async_smem();
+      tr.ev(38);
       tc_fence_before();
       mbar_arrive(&p_ready[g]);
       tr.ev(35);
@@ -803,6 +807,256 @@ attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   if (warp == SMW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if (p.cta_trace && threadIdx.x == 0) {
+    unsigned long long* t = p.cta_trace + 4 * ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    t[0] = cta_t0;
+    t[1] = globaltimer_ns();
+    t[2] = smid();
+    t[3] = static_cast<unsigned long long>(clock64());
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Co-resident prefill kernel (head_dim 64 / 128): ONE 128-row q tile per CTA, TWO CTAs per SM.
+// The exponentials (MUFU.EX2, 8 cycles per warp instruction per SM sub-partition) bound attention at these head
+// sizes.  Two independent CTAs on an SM drift out of phase on their own, so one CTA's exp phase overlaps the
+// other's TMEM loads / row max / barrier waits / prologue / epilogue -- the two-q-tiles-in-one-CTA kernel above keeps
+// its tiles in lockstep through the single in-order MMA issuer and leaves the XU pipe idle ~45% of the time.
+// 256 threads = 2 warpgroups (setmaxnreg is per warpgroup):
+//   warps 0-3   softmax / correction / epilogue (thread = q row = TMEM lane; the whole S row lives in registers)
+//   warp  4     TMA producer: Q once; K through a 2-slot ring, V through a 1-slot ring, issued in the order
+//               K0 K1 V0 | K(j+2) V(j+1) ... so a load never queues behind one that waits for a later event
+//   warp  5     tcgen05.mma issuer:  S(j+1) = Q.K(j+1)^T as soon as S(j) is in registers, then O += P(j).V(j)
+//   warps 6-7   idle (complete the second warpgroup)
+// smem per CTA (head_dim 64): Q 16K + K 2x16K + V 16K + P 32K = 96 KB  -> 2 CTAs / SM;  TMEM 256 columns per CTA.
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+struct AttnCoCfg {
+  static constexpr int BNKV = (HD == 64) ? 128 : 64;
+  static constexpr int K_STAGES = 2;
+  static constexpr int Q_BYTES = ATT_BM * HD * 2;
+  static constexpr int KV_BYTES = BNKV * HD * 2;
+  static constexpr int P_BYTES = ATT_BM * BNKV * 2;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = Q_BYTES + (K_STAGES + 1) * KV_BYTES + P_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 256;
+  static_assert(BNKV + HD <= 256, "TMEM budget");
+  static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
+};
+constexpr int ATT_CO_THREADS = 256;
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_CO_THREADS, 2)
+attn_prefill_co_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCoCfg<HD>;
+  constexpr int BNKV = Cfg::BNKV;
+  constexpr int HB = HD / 64;
+  constexpr int SCH = BNKV / 32;
+  constexpr int OCH = HD / 32;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;                      // [2]
+  uint8_t* sV = sK + Cfg::K_STAGES * Cfg::KV_BYTES;     // [1]
+  uint8_t* sP = sV + Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bar_q = bars;
+  uint64_t* k_full = bars + 1;       // [2]
+  uint64_t* k_empty = bars + 3;      // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 6;
+  uint64_t* s_full = bars + 7;       // S written by the tensor core
+  uint64_t* s_free = bars + 8;       // S copied to registers by all 128 softmax threads
+  uint64_t* p_ready = bars + 9;      // P written to smem by all 128 softmax threads
+  uint64_t* o_done = bars + 10;      // O += P.V finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long cta_t0 = 0;
+  if (p.cta_trace && threadIdx.x == 0) cta_t0 = globaltimer_ns();
+  const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
+  const int qt = n_qt - 1 - static_cast<int>(blockIdx.x);   // heaviest (latest) q tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.NH / p.NKV);
+  const int q0 = qt * ATT_BM;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < Cfg::K_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_ready, 128);
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                               // Q/K/V and the cache length come from the preceding kernels
+  const int t0 = *p.t0_ptr;
+  const int T = t0 + p.S;
+  int kv_end = T;
+  if (p.causal) kv_end = min(T, t0 + q0 + ATT_BM);
+  int kv_begin = 0;
+  if (p.window > 0) kv_begin = max(0, t0 + q0 - p.window + 1);
+  const int jt0 = kv_begin / BNKV;
+  const int jt1 = (kv_end + BNKV - 1) / BNKV;               // kv tiles [jt0, jt1)
+  const int n_tiles = jt1 - jt0;
+  const uint32_t tS = tmem_base;            // S accumulator columns [0, BNKV)
+  const uint32_t tO = tmem_base + BNKV;     // O accumulator columns [BNKV, BNKV + HD)
+
+  if (warp >= 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 4) {
+      // ------------------------------ TMA producer ------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb)
+          tma_load_2d(sQ + hb * (ATT_BM * 128), &tmap_q, bar_q, h * HD + hb * 64, b * p.S + q0, kEvictFirst);
+        const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
+        auto load_k = [&](int it) {               // it = tile index relative to jt0
+          const int st = it & 1;
+          mbar_wait(&k_empty[st], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sK + st * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[st], hb * 64,
+                        kv_row0 + (jt0 + it) * BNKV, kEvictLast);
+        };
+        auto load_v = [&](int it) {
+          mbar_wait(v_empty, (it & 1) ^ 1);
+          mbar_expect_tx(v_full, Cfg::KV_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sV + hb * (BNKV * 128), &tmap_v, v_full, hb * 64, kv_row0 + (jt0 + it) * BNKV, kEvictLast);
+        };
+        if (n_tiles > 0) load_k(0);
+        if (n_tiles > 1) load_k(1);
+        if (n_tiles > 0) load_v(0);
+        for (int it = 0; it < n_tiles; ++it) {
+          if (it + 2 < n_tiles) load_k(it + 2);   // slot freed by S(it)
+          if (it + 1 < n_tiles) load_v(it + 1);   // slot freed by P.V(it)
+        }
+      }
+    } else if (warp == 5) {
+      // ------------------------------ MMA issuer ------------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // P (K-major) x V (MN-major)
+        auto issue_s = [&](int it) {
+          const int st = it & 1;
+          mbar_wait(&k_full[st], (it >> 1) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sK + st * Cfg::KV_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tS, umma_smem_desc(smem_u32(sQ) + hb * (ATT_BM * 128) + k * 32, 16, 1024),
+                           umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024), idesc_s, (hb | k) != 0 ? 1u : 0u);
+          umma_commit(&k_empty[st]);
+          umma_commit(s_full);
+        };
+        AttTrace tr;
+        tr.init(p.trace, 0);
+        tr.ev(0);
+        mbar_wait(bar_q, 0);
+        tr.ev(1);
+        if (n_tiles > 0) issue_s(0);
+        for (int it = 0; it < n_tiles; ++it) {
+          if (it + 1 < n_tiles) {
+            mbar_wait(s_free, it & 1);              // S(it) is in registers
+            tr.ev(10);
+            issue_s(it + 1);
+            tr.ev(12);
+          }
+          mbar_wait(p_ready, it & 1);
+          tr.ev(20);
+          mbar_wait(v_full, it & 1);
+          tr.ev(21);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sV);
+#pragma unroll
+          for (int kk = 0; kk < BNKV / 16; ++kk)
+            umma_bf16_ss(tO, umma_smem_desc(smem_u32(sP) + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
+                         umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (it | kk) != 0 ? 1u : 0u);
+          umma_commit(v_empty);
+          umma_commit(o_done);
+          tr.ev(22);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax / correction / epilogue ------------------------------
+    setmaxnreg_inc<216>();
+    const int r = warp * 32 + lane;                 // q row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int qpos = t0 + q0 + r;
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = p.scale * LOG2E;
+    const bool cap = p.softcap > 0.f;
+    const float cap_in = cap ? p.scale / p.softcap : 0.f, cap_out = p.softcap * LOG2E;
+    float m_used = -INFINITY, l = 0.f;
+    AttTrace tr;
+    tr.init((warp == 0 && lane == 0) ? p.trace : nullptr, 1);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int kv0 = (jt0 + it) * BNKV;
+      const bool need_mask = (p.causal && kv0 + BNKV - 1 > t0 + q0) || (kv0 + BNKV > T) ||
+                             (p.window > 0 && kv0 < t0 + q0 + ATT_BM - p.window);
+      int lo = 0, hi = BNKV;
+      if (need_mask) {
+        int last = T - 1;
+        if (p.causal) last = min(last, qpos);
+        hi = min(BNKV, last - kv0 + 1);
+        if (p.window > 0) lo = max(0, qpos - p.window + 1 - kv0);
+      }
+      const unsigned span = hi > lo ? static_cast<unsigned>(hi - lo) : 0u;
+      tr.ev(30);
+      mbar_wait(s_full, it & 1);
+      tr.ev(31);
+      tc_fence_after();
+      att_softmax_tile<SCH, OCH>(tS + lane_off, tO + lane_off, sP, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l,
+                                 it > 0, o_done, (it - 1) & 1, s_free, nullptr, &tr);
+      fence_proxy_async_smem();
+      tr.ev(38);
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      tr.ev(35);
+    }
+    if (n_tiles > 0) {
+      mbar_wait(o_done, (n_tiles - 1) & 1);
+      tc_fence_after();
+    }
+    att_store_out<OCH>(tO + lane_off, n_tiles > 0, l, (q0 + r) < p.S,
+                       p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if (p.cta_trace && threadIdx.x == 0) {
+    unsigned long long* t = p.cta_trace + 4 * ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    t[0] = cta_t0;
+    t[1] = globaltimer_ns();
+    t[2] = smid();
+    t[3] = static_cast<unsigned long long>(clock64());
   }
 }
 

@@ -36,6 +36,16 @@ __device__ __forceinline__ bool elect_one() {
 // draining.  pdl_trigger() lets the NEXT kernel start early; pdl_wait() blocks until the PREVIOUS kernel has
 // completed and its memory is visible -- it must precede every access to data the predecessor produced.
 // Both are no-ops for ordinary launches.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -89,6 +99,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 24)) {   // >= hundreds of ms even if every probe returned immediately
       printf("b2: mbarrier wait timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// Low-latency wait for single-thread roles (MMA issuer): mbarrier.test_wait polled in a loop.  The hardware-suspended
+// try_wait above wakes ~200-400 cycles after the last arrival, which sits on the softmax -> P.V -> softmax chain.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("b2: mbarrier spin-wait timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
     }
   }
@@ -259,6 +292,11 @@ __device__ __forceinline__ float poly_exp2(float x) {
   p = fmaf(p, f, 0.693252682685852f);
   p = fmaf(p, f, 0.9999276399612427f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;

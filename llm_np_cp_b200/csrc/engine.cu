@@ -60,6 +60,8 @@ extern "C" int b2_device_count(void) {
 }
 
 static int require_gpu(int device) {
+  static bool ok[64] = {};                     // a device that passed once is not re-queried (cudaGetDeviceProperties is ~1 ms)
+  if (device >= 0 && device < 64 && ok[device]) return B2_OK;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
     cudaGetLastError();
@@ -70,6 +72,7 @@ static int require_gpu(int device) {
   CK(cudaGetDeviceProperties(&p, device));
   if (p.major != 10)
     return fail(B2_ERR_NO_GPU, "device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
+  if (device < 64) ok[device] = true;
   return B2_OK;
 }
 
@@ -275,6 +278,23 @@ static int launch_attn_pair_t(const CUtensorMap& tq, const CUtensorMap& tk, cons
   return B2_OK;
 }
 
+template <int HD>
+static int launch_attn_co_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                            cudaStream_t st) {
+  auto kern = attn_prefill_co_kernel<HD>;
+  static bool attr[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || !attr[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCoCfg<HD>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (dev < 16) attr[dev] = true;
+  }
+  dim3 grid((p.S + ATT_BM - 1) / ATT_BM, p.NH, p.B);
+  CK(launch_k(kern, grid, dim3(ATT_CO_THREADS), AttnCoCfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
+  return B2_OK;
+}
+
 // prefill attention dispatch: the pipelined two-q-tile kernel for head_dim 64/128 (unless B2_ATTN_SINGLE is set
 // or the sequence fits one q tile), the single-tile kernel otherwise (head_dim 256: TMEM/smem budget).
 static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, const AttnParams& p_in, int HD,
@@ -283,6 +303,7 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
   AttnParams p = p_in;
   if (const char* ev = getenv("B2_V_LBO")) p.v_lbo = atoi(ev);   // bring-up knobs for the MN-major V descriptor
   if (const char* ev = getenv("B2_V_SBO")) p.v_sbo = atoi(ev);
+  if (const char* ev = getenv("B2_ATT_CTATRACE")) p.cta_trace = reinterpret_cast<unsigned long long*>(strtoull(ev, nullptr, 0));
   if (const char* ev = getenv("B2_ATT_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(ev, nullptr, 0));   // device pointer (diagnostics)
   static const bool force_single = getenv("B2_ATTN_SINGLE") != nullptr;
   const bool precise = p.q_lo_col != 0;
@@ -298,6 +319,8 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
     if (HD == 128) return launch_attn_t<128, 2>(tq, tk, tv, p, st);
     return fail(B2_ERR_ARG, "precise mode supports head_dim 64 and 128 only");
   }
+  static const bool use_co = getenv("B2_ATTN_PAIR") == nullptr;   // default: one q tile per CTA, two CTAs per SM
+  if (pair && use_co) return HD == 64 ? launch_attn_co_t<64>(tq, tk, tv, p, st) : launch_attn_co_t<128>(tq, tk, tv, p, st);
   if (pair) {
     static const int split = getenv("B2_ATTN_SPLIT") ? atoi(getenv("B2_ATTN_SPLIT")) : 1;   // softmax threads per q row (2 measured slower: the XU pipe, not latency, bounds the exp phase)
     if (split == 2) return HD == 64 ? launch_attn_pair_t<64, 2>(tq, tk, tv, p, st) : launch_attn_pair_t<128, 2>(tq, tk, tv, p, st);

@@ -240,9 +240,56 @@ def stage_attn_trace():
                 if a == 32 and 31 in last: d["ld S -> regs"].append(c - last[31])
                 if a == 33 and 32 in last: d["row max"].append(c - last[32])
                 if a == 34 and 33 in last: d["wait o_done"].append(c - last[33])
-                if a == 35: d["exp+P write"].append(c - last.get(34, last.get(33, c)))
+                if a == 37: d["exp loop"].append(c - last.get(34, last.get(33, c)))
+                if a == 38 and 37 in last: d["fence.proxy"].append(c - last[37])
+                if a == 35 and 38 in last: d["arrive p_ready"].append(c - last[38])
             for k2, v in d.items():
                 print(f"   [{nm}] {k2:14s} mean {np.mean(v):8.1f}  max {max(v):6d}  n={len(v)}")
+
+
+def stage_attn_cta():
+    """Per-CTA {start, end, smid} of the pair kernel: where the kernel's wall time goes (busy vs gaps vs tail)."""
+    from gpu_util import bf16_randn, L, stream
+    from llm_np_cp_b200 import _lib
+    for (B, S, NH, NKV, HD) in [(8, 2048, 32, 8, 64), (1, 8192, 24, 8, 128)]:
+        q = bf16_randn(B * S, NH * HD, seed=13)
+        kc, vc = bf16_randn(B, NKV, S, HD, seed=14), bf16_randn(B, NKV, S, HD, seed=15)
+        out = torch.zeros((B * S, NH * HD), dtype=torch.bfloat16, device="cuda")
+        npair = S // 128 if (not os.environ.get('B2_ATTN_PAIR')) else (S // 128 + 1) // 2
+        ncta = npair * NH * B
+        tb = torch.zeros(ncta * 4, dtype=torch.int64, device="cuda")
+        os.environ["B2_ATT_CTATRACE"] = hex(tb.data_ptr())
+        for _ in range(3):
+            tb.zero_()
+            _lib.check(L().b2_op_attention(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), out.data_ptr(), B, S, NH, NKV, HD, S, 0,
+                                           float(1 / math.sqrt(HD)), 0.0, 1, 0, 0, stream()))
+            torch.cuda.synchronize()
+        del os.environ["B2_ATT_CTATRACE"]
+        t = tb.cpu().numpy().reshape(ncta, 4)
+        st, en, sm = t[:, 0], t[:, 1], t[:, 2]
+        T0, T1 = st.min(), en.max()
+        dur = (en - st).astype(np.float64)
+        print(f"== attn B{B} S{S} NH{NH} HD{HD}: {ncta} CTAs, kernel span {(T1 - T0) / 1e3:.1f} us, sum(CTA time)/148 = {dur.sum() / 148 / 1e3:.1f} us")
+        x = np.arange(ncta) % npair           # blockIdx.x (pair index reversed: 0 = heaviest)
+        for bx in range(npair):
+            d = dur[x == bx]
+            iters = (npair - bx) if (not os.environ.get('B2_ATTN_PAIR')) else 2 * (npair - 1 - bx) + 2
+            print(f"   blockIdx.x {bx:2d} ({iters:3d} kv iters): mean {d.mean() / 1e3:7.2f} us  min {d.min() / 1e3:7.2f}  max {d.max() / 1e3:7.2f}")
+        gaps, busy, last_end, ghz = [], [], [], []
+        for s_ in np.unique(sm):
+            idx = np.where(sm == s_)[0]
+            o = idx[np.argsort(st[idx])]
+            if len(o) > 1 and en[o[-1]] > en[o[0]]:
+                ghz.append((t[o[-1], 3] - t[o[0], 3]) / float(en[o[-1]] - en[o[0]]))
+            busy.append(dur[o].sum())
+            last_end.append(en[o].max())
+            gaps += list((st[o][1:] - en[o][:-1]).astype(np.float64))
+            gaps.append(float(st[o][0] - T0))
+        gaps = np.array(gaps)
+        print(f"   SM clock from clock64/globaltimer: {np.median(ghz):.3f} GHz")
+        print(f"   SMs used {len(busy)}; busy/span mean {np.mean(busy) / (T1 - T0):.3f} min {np.min(busy) / (T1 - T0):.3f}; "
+              f"inter-CTA gap mean {gaps.mean():.0f} ns, p50 {np.median(gaps):.0f}, max {gaps.max():.0f}, total/SM {gaps.sum() / len(busy) / 1e3:.1f} us; "
+              f"tail (span - SM's last end) mean {np.mean(T1 - np.array(last_end)) / 1e3:.1f} us")
 
 
 def stage_gemm2():
