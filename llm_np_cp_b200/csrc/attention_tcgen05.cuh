@@ -1229,4 +1229,231 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split-KV GQA decode attention (q_len == 1, long caches).  The per-(batch, q head) kernel above walks the cache
+// serially with one memory round trip per 8 positions and reads K/V once per Q head; at T ~ 2K that is ~6x off the
+// HBM roofline.  Here a CTA owns (T-slice, kv head, batch) and serves ALL n_rep = NH/NKV query heads of the kv head
+// from one pass over K/V (the GQA reuse the reference materialises with repeat_kv, llama3.2_model_numpy.py:188-204,
+// :470-471):
+//   warp 4      producer: 64-position K and V tiles through a shared-memory ring (TMA, 128B swizzle)
+//   warps 0-3   consumers: warp w owns positions [16w, 16w+16) of every tile.  The n_rep query heads are the rows of
+//               a 16-row MMA tile: S = Q.K^T and O += P.V run on the tensor cores with mma.sync.m16n8k16 (ldmatrix
+//               fragments straight from the swizzled tiles) -- ~4 instructions per position instead of ~35 on the
+//               FMA pipe -- with a per-row online softmax on the accumulator fragments.
+// Partial (m, l, o[HD]) per (head, slice) go to a scratch buffer; the LAST CTA to finish a (batch, kv head) -- found
+// with a counter -- merges the slices in fixed order (deterministic) and writes bf16.  Grid = (slices, NKV, B).
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+struct DecSplitCfg {
+  static constexpr int TP = 64;                  // positions per tile
+  static constexpr int STAGES = (HD == 64) ? 4 : (HD == 128 ? 3 : 2);
+  static constexpr int HB = HD / 64;             // 64-column (128-byte) blocks per row
+  static constexpr int TILE_BYTES = TP * HD * 2; // one K or V tile
+  static constexpr int SMEM_BYTES = 2 * STAGES * TILE_BYTES + 128 + 1024;
+};
+constexpr int DEC_SPLIT_THREADS = 160;
+constexpr int DEC_MAX_SPLITS = 16;
+constexpr int DEC_MAX_NREP = 8;                  // query heads per kv head served by rows 0..7 of the MMA tile
+
+template <int HD>
+__global__ void __launch_bounds__(DEC_SPLIT_THREADS)
+attn_decode_split_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                         const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* __restrict__ out, int ldo, int NKV,
+                         int nrep, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap, int window,
+                         float* __restrict__ part, int* __restrict__ counters) {
+  using Cfg = DecSplitCfg<HD>;
+  constexpr int TP = Cfg::TP, STAGES = Cfg::STAGES, HB = Cfg::HB, TILE_BYTES = Cfg::TILE_BYTES;
+  constexpr int KS = HD / 16;                    // k-steps of S = Q.K^T
+  constexpr int NT = HD / 8;                     // 8-column n-tiles of O
+  constexpr int PW = HD + 2;                     // floats per partial: o[HD], m, l
+  static_assert(4 * DEC_MAX_NREP * PW * 4 <= 2 * STAGES * TILE_BYTES, "merge area aliases the K/V ring");
+  extern __shared__ uint8_t dsm_raw[];
+  uint8_t* dsm = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
+  uint8_t* sK = dsm;
+  uint8_t* sV = dsm + STAGES * TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + 2 * STAGES * TILE_BYTES);
+  uint64_t* empty = full + STAGES;
+  int* s_flag = reinterpret_cast<int*>(empty + STAGES);
+  float* s_merge = reinterpret_cast<float*>(dsm);          // [4 warps][DEC_MAX_NREP][PW], valid after the main loop only
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsplit = gridDim.x, sp = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  pdl_trigger();
+  __syncthreads();
+  pdl_wait();
+  const int T = *t0_ptr + 1;                     // this step's token is already appended
+  const int qpos = T - 1;
+  const int kv_begin = (window > 0) ? max(0, qpos - window + 1) : 0;
+  const int len = T - kv_begin;
+  const int per = (((len + nsplit - 1) / nsplit) + TP - 1) / TP * TP;     // positions per slice, whole tiles
+  const int t_lo = kv_begin + sp * per;
+  const int t_hi = min(T, t_lo + per);
+  const int n_tiles = t_hi > t_lo ? (t_hi - t_lo + TP - 1) / TP : 0;
+  const int row0 = (b * NKV + kvh) * Tmax;
+
+  const int g = lane >> 2, tq = lane & 3;        // MMA fragment coordinates: row g (= query head), column pair tq
+  float m_row = -INFINITY, l_row = 0.f;          // row g's running max (log2 units) / this thread's share of the row sum
+  float o[NT][4];
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = 0; i < n_tiles; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(&empty[st], ((i / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[st], 2 * TILE_BYTES);
+        const int t = t_lo + i * TP;
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb) {
+          tma_load_2d(sK + st * TILE_BYTES + hb * (TP * 128), &tmap_k, &full[st], hb * 64, row0 + t, kEvictFirst);
+          tma_load_2d(sV + st * TILE_BYTES + hb * (TP * 128), &tmap_v, &full[st], hb * 64, row0 + t, kEvictFirst);
+        }
+      }
+    }
+  } else {
+    // A fragments of Q: row g = head kvh*nrep + g (zero rows beyond nrep), k = head dims
+    uint32_t qa[KS][2];
+    {
+      const __nv_bfloat16* qrow = q + static_cast<size_t>(b) * ldq + (kvh * nrep + g) * HD;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        qa[ks][0] = (g < nrep) ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 2 * tq)) : 0u;
+        qa[ks][1] = (g < nrep) ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + 2 * tq)) : 0u;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = scale * LOG2E;
+    const int p0 = warp * 16;                    // this warp's positions inside a tile
+    // ldmatrix row addresses (swizzled): K fragments: lane -> (row p0 + nt*8 + lane%8, chunk 4*half + lane/8)
+    const int lrow = lane & 7, lsel = lane >> 3;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(&full[st], (i / STAGES) & 1);
+      const int tpos = t_lo + i * TP + p0;       // absolute position of this warp's first row
+      if (tpos < t_hi) {
+        const uint32_t kb = smem_u32(sK + st * TILE_BYTES), vb = smem_u32(sV + st * TILE_BYTES);
+        float sc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+          const int r = p0 + nt * 8 + lrow;
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t b0, b1, b2, b3;
+              ldmatrix_x4(kb + hb * (TP * 128) + r * 128 + (((4 * half + lsel) ^ (r & 7)) << 4), b0, b1, b2, b3);
+              const int ks = hb * 4 + half * 2;
+              mma_bf16_16816(sc[nt], qa[ks][0], 0u, qa[ks][1], 0u, b0, b1);
+              mma_bf16_16816(sc[nt], qa[ks + 1][0], 0u, qa[ks + 1][1], 0u, b2, b3);
+            }
+        }
+        // row g's four scores: positions tpos + nt*8 + 2*tq + {0, 1}
+        float x[4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float v = sc[nt][e];
+            if (softcap > 0.f) v = softcap * LOG2E * tanhf(v * scale / softcap);
+            else v *= sl2;
+            x[nt * 2 + e] = (tpos + nt * 8 + 2 * tq + e < t_hi) ? v : -INFINITY;
+          }
+        float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_row, mx);    // finite: position tpos is valid for every row
+        const float alpha = fast_exp2(m_row - m_new);
+        float pe[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pe[e] = fast_exp2(x[e] - m_new);
+        l_row = l_row * alpha + (pe[0] + pe[1]) + (pe[2] + pe[3]);
+        m_row = m_new;
+        if (alpha != 1.0f) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) o[nt][0] *= alpha, o[nt][1] *= alpha;
+        }
+        // P as the A fragment of O += P.V (k = this warp's 16 positions); rows 8..15 are unused -> 0
+        const uint32_t pa0 = pack_bf16(pe[0], pe[1]), pa2 = pack_bf16(pe[2], pe[3]);
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {    // two 8-column n-tiles (16 head dims) per ldmatrix.x4.trans
+          const int chunk = (2 * np) & 7, hb = (2 * np) >> 3;
+          const int r = p0 + lrow + 8 * (lsel & 1);
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(vb + hb * (TP * 128) + r * 128 + (((chunk + (lsel >> 1)) ^ (r & 7)) << 4), b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
+          mma_bf16_16816(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    l_row += __shfl_xor_sync(0xffffffffu, l_row, 1);
+    l_row += __shfl_xor_sync(0xffffffffu, l_row, 2);
+  }
+  __syncthreads();                               // every warp is done with the K/V ring: reuse it for the merge
+  if (warp < 4 && g < nrep) {
+    float* d = s_merge + (warp * DEC_MAX_NREP + g) * PW;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      d[nt * 8 + 2 * tq] = o[nt][0];
+      d[nt * 8 + 2 * tq + 1] = o[nt][1];
+    }
+    if (tq == 0) d[HD] = m_row, d[HD + 1] = l_row;
+  }
+  __syncthreads();
+  const size_t pbase = (static_cast<size_t>(b * NKV + kvh) * nrep) * nsplit;
+  for (int idx = threadIdx.x; idx < nrep * HD; idx += DEC_SPLIT_THREADS) {
+    const int j = idx / HD, d = idx - j * HD;
+    float m_all = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) m_all = fmaxf(m_all, s_merge[(w * DEC_MAX_NREP + j) * PW + HD]);
+    float acc = 0.f, ls = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = s_merge[(w * DEC_MAX_NREP + j) * PW + HD];
+      const float wgt = (mw == -INFINITY) ? 0.f : fast_exp2(mw - m_all);
+      acc = fmaf(wgt, s_merge[(w * DEC_MAX_NREP + j) * PW + d], acc);
+      ls = fmaf(wgt, s_merge[(w * DEC_MAX_NREP + j) * PW + HD + 1], ls);
+    }
+    float* pr = part + ((pbase + static_cast<size_t>(j) * nsplit) + sp) * PW;
+    pr[d] = acc;
+    if (d == 0) pr[HD] = m_all, pr[HD + 1] = ls;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&counters[b * NKV + kvh], 1);
+    *s_flag = (prev == nsplit - 1);
+  }
+  __syncthreads();
+  if (*s_flag) {                                 // last slice of this (batch, kv head): merge all slices, fixed order
+    __threadfence();
+    for (int idx = threadIdx.x; idx < nrep * HD; idx += DEC_SPLIT_THREADS) {
+      const int j = idx / HD, d = idx - j * HD;
+      const float* pj = part + (pbase + static_cast<size_t>(j) * nsplit) * PW;
+      float m_all = -INFINITY;
+      for (int s = 0; s < nsplit; ++s) m_all = fmaxf(m_all, __ldcg(pj + s * PW + HD));
+      float acc = 0.f, ls = 0.f;
+      for (int s = 0; s < nsplit; ++s) {
+        const float ms = __ldcg(pj + s * PW + HD);
+        const float wgt = (ms == -INFINITY) ? 0.f : fast_exp2(ms - m_all);
+        acc = fmaf(wgt, __ldcg(pj + s * PW + d), acc);
+        ls = fmaf(wgt, __ldcg(pj + s * PW + HD + 1), ls);
+      }
+      out[static_cast<size_t>(b) * ldo + (kvh * nrep + j) * HD + d] = __float2bfloat16_rn(ls > 0.f ? acc / ls : 0.f);
+    }
+    if (threadIdx.x == 0) counters[b * NKV + kvh] = 0;     // self-cleaning: ready for the next launch
+  }
+}
+
 }  // namespace b2

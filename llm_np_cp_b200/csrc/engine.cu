@@ -332,9 +332,55 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
   return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", HD);
 }
 
+// number of T-slices of the split-KV decode kernel for a cache of Tmax positions (fixed per cache so the decode CUDA
+// graph keeps its grid): ~8 tiles per CTA, at least ~2 CTAs per SM, never more slices than tiles.
+// B2_DECODE_SPLIT_MIN_T=n sends caches of <= n positions to the one-warp-per-(batch, head) kernel instead (bring-up).
+static int decode_splits(int B, int NKV, int Tmax) {
+  static const int min_t = getenv("B2_DECODE_SPLIT_MIN_T") ? atoi(getenv("B2_DECODE_SPLIT_MIN_T")) : 0;
+  if (Tmax <= min_t) return 0;
+  const int tiles = (Tmax + 63) / 64;
+  int ns = (tiles + 7) / 8;
+  const int want = (2 * 148 + B * NKV - 1) / (B * NKV);
+  if (ns < want) ns = want;
+  if (ns > tiles) ns = tiles;
+  if (ns > DEC_MAX_SPLITS) ns = DEC_MAX_SPLITS;
+  return ns < 1 ? 1 : ns;
+}
+static size_t decode_part_floats(int B, int NH, int HD) { return static_cast<size_t>(B) * NH * DEC_MAX_SPLITS * (HD + 2); }
+
+template <int HD>
+static int launch_decode_split(const bf16* q, int ldq, const bf16* kc, const bf16* vc, bf16* out, int ldo, int B, int NKV,
+                               int nrep, int Tmax, const int* t0_ptr, float scale, float softcap, int window, float* part,
+                               int* cnt, int nsplit, cudaStream_t st) {
+  auto kern = attn_decode_split_kernel<HD>;
+  static bool attr[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || !attr[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DecSplitCfg<HD>::SMEM_BYTES));
+    if (dev < 16) attr[dev] = true;
+  }
+  CUtensorMap tk, tv;
+  const uint64_t kv_rows = static_cast<uint64_t>(B) * NKV * Tmax;
+  CKR(make_tmap(&tk, kc, kv_rows, HD, HD, 64));
+  CKR(make_tmap(&tv, vc, kv_rows, HD, HD, 64));
+  CK(launch_k(kern, dim3(nsplit, NKV, B), dim3(DEC_SPLIT_THREADS), DecSplitCfg<HD>::SMEM_BYTES, st, tk, tv, q, ldq, out, ldo,
+              NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt));
+  return B2_OK;
+}
+
+// decode attention dispatch: the split-KV GQA tensor-core kernel when scratch is supplied (plain bf16, n_rep <= 8,
+// long cache), else the one-warp-per-(batch, head) kernel (precise mode, short caches, unusual head ratios)
 static int attn_decode(const bf16* q, int ldq, const bf16* kc, const bf16* vc, bf16* out, int ldo, int B, int NH,
                        int NKV, int HD, int Tmax, const int* t0_ptr, float scale, float softcap, int window,
-                       cudaStream_t st, int q_lo_col = 0, size_t kv_lo_off = 0, int out_lo_col = 0) {
+                       cudaStream_t st, int q_lo_col = 0, size_t kv_lo_off = 0, int out_lo_col = 0, float* part = nullptr,
+                       int* cnt = nullptr, int nsplit = 0) {
+  const int nrep = NH / NKV;
+  if (part && cnt && nsplit > 0 && !q_lo_col && nrep >= 1 && nrep <= DEC_MAX_NREP) {
+    if (HD == 64) return launch_decode_split<64>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st);
+    if (HD == 128) return launch_decode_split<128>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st);
+    if (HD == 256) return launch_decode_split<256>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st);
+  }
   const int grid = (B * NH + 3) / 4;
 #define DEC(HD_)                                                                                              \
   if (HD == HD_) {                                                                                            \
@@ -409,6 +455,9 @@ struct b2_cache {
   int* t0_dev;
   size_t plane;  // elements per (layer, k|v) plane
   int pf;        // planes per tensor: 1, or 2 in precise mode (hi plane followed by lo plane)
+  float* dec_part = nullptr;   // split-KV decode partials [max_batch][NH][DEC_MAX_SPLITS][HD+2]
+  int* dec_cnt = nullptr;      // per (batch, kv head) arrival counters (self-resetting)
+  int dec_splits = 0;
 };
 
 struct GraphKey {
@@ -583,6 +632,8 @@ extern "C" void b2_cache_destroy(b2_cache* c) {
   if (!c) return;
   cudaFree(c->kv);
   cudaFree(c->t0_dev);
+  cudaFree(c->dec_part);
+  cudaFree(c->dec_cnt);
   delete c;
 }
 
@@ -744,6 +795,12 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
   CK(cudaMalloc(&c->t0_dev, 4));
   CK(cudaMemset(c->t0_dev, 0, 4));
+  if (!e->cfg.precise) {
+    c->dec_splits = decode_splits(max_batch, e->cfg.num_key_value_heads, max_tokens);
+    CK(cudaMalloc(&c->dec_part, decode_part_floats(max_batch, e->cfg.num_attention_heads, e->cfg.head_dim) * 4));
+    CK(cudaMalloc(&c->dec_cnt, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
+    CK(cudaMemset(c->dec_cnt, 0, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
+  }
   CK(cudaDeviceSynchronize());       // cudaMemset is asynchronous; callers may use non-blocking streams
   *out = c;
   return B2_OK;
@@ -894,7 +951,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
     if (decode) {
       CKR(attn_decode(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, pf * e->q_cols, B, c.num_attention_heads,
                       c.num_key_value_heads, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st,
-                      c.precise ? e->q_cols : 0, c.precise ? cache->plane : 0, c.precise ? e->q_cols : 0));
+                      c.precise ? e->q_cols : 0, c.precise ? cache->plane : 0, c.precise ? e->q_cols : 0, cache->dec_part,
+                      cache->dec_cnt, cache->dec_splits));
       e->st.launches++;
     } else {
       AttnParams a;
@@ -1276,8 +1334,18 @@ extern "C" int b2_op_attention(const void* q, const void* kc, const void* vc, vo
   int r;
   if (decode) {
     if (S != 1) { cudaFree(dt0); return fail(B2_ERR_ARG, "decode attention needs S == 1"); }
+    float* part = nullptr;
+    int* cnt = nullptr;
+    CK(cudaMalloc(&part, decode_part_floats(B, NH, HD) * 4));
+    CK(cudaMalloc(&cnt, static_cast<size_t>(B) * NKV * 4));
+    CK(cudaMemset(cnt, 0, static_cast<size_t>(B) * NKV * 4));
+    CK(cudaDeviceSynchronize());
     r = attn_decode(static_cast<const bf16*>(q), NH * HD, static_cast<const bf16*>(kc), static_cast<const bf16*>(vc),
-                    static_cast<bf16*>(out), NH * HD, B, NH, NKV, HD, Tmax, dt0, scale, softcap, window, st);
+                    static_cast<bf16*>(out), NH * HD, B, NH, NKV, HD, Tmax, dt0, scale, softcap, window, st, 0, 0, 0, part, cnt,
+                    decode_splits(B, NKV, Tmax));
+    cudaStreamSynchronize(st);
+    cudaFree(part);
+    cudaFree(cnt);
   } else {
     AttnParams a;
     memset(&a, 0, sizeof(a));

@@ -308,7 +308,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // everything above overlapped the previous kernel's tail; operands are only touched below
+  // Everything above overlapped the previous kernel's tail (PDL).  The wait for the previous kernel sits inside the
+  // roles: the producer first streams the W tiles of its first k-steps (weights are constants, nothing in the stream
+  // writes them) and only then waits to load activations; the epilogue warps wait before they touch global memory;
+  // the MMA issuer only ever sees shared memory through the barriers.
 
   auto tile_coords = [&](int tile, int& mb, int& nb, int& kb0) {
     kb0 = (tile % p.split_k) * KB;
@@ -324,16 +327,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int pre = 0;                               // ring slots whose W tile is already in flight (first tile only)
+      if (static_cast<int>(blockIdx.x) < total) {
+        int mb, nb, kb0;
+        tile_coords(blockIdx.x, mb, nb, kb0);
+        pre = KB < STAGES ? KB : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_expect_tx(&full[kb], Cfg::A_BYTES + Cfg::B_BYTES);
+          const int ka = (kb0 + kb) * GEMM_BK;
+          const int kw = ka >= p.k_wrap ? ka - p.k_wrap : ka;
+          tma_load_2d(sB + kb * Cfg::B_BYTES, &tmap_b, &full[kb], kw, nb * BN, kEvictNormal);
+        }
+      }
+      pdl_wait();                                // activations come from the preceding kernels
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         int mb, nb, kb0;
         tile_coords(tile, mb, nb, kb0);
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           const int ka = (kb0 + kb) * GEMM_BK;
           const int kw = ka >= p.k_wrap ? ka - p.k_wrap : ka;
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_a, &full[stage], ka, mb * GEMM_BM, kEvictNormal);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_b, &full[stage], kw, nb * BN, kEvictNormal);
+          if (pre > 0) {                         // slot armed and W requested above: only the activations are missing
+            --pre;
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_a, &full[stage], ka, mb * GEMM_BM, kEvictNormal);
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_a, &full[stage], ka, mb * GEMM_BM, kEvictNormal);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_b, &full[stage], kw, nb * BN, kEvictNormal);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -378,6 +399,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = ew >> 2;                // two warps share a quarter; each takes every other column group
     uint8_t* slab = sStage + ew * 4096;
     uint32_t acc = 0, acc_phase = 0;
+    pdl_wait();                                // residual / tables are read and outputs written only after this
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int mb, nb, kb0;
       tile_coords(tile, mb, nb, kb0);

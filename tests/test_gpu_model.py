@@ -90,6 +90,27 @@ def test_decode_graph_matches_plain():
     assert np.array_equal(outs[0], outs[1])        # same kernels, same order: bit-identical
 
 
+@pytest.mark.parametrize("family,graph", [("llama", False), ("llama", True), ("gemma2", False)])
+def test_decode_long_cache_vs_oracle(family, graph):
+    """Long caches decode through several T-slices of the split-KV tensor-core attention kernel (merged by the last
+    CTA); same parity bar as every other path, against the NumPy oracle on the same seeded inputs."""
+    cfg = (O.gemma2_config if family == "gemma2" else O.llama_config)("tiny")
+    w = O.synth_weights(cfg, 5, 0.08, 0.1)
+    model = (M.Gemma2ForCausalLM if family == "gemma2" else M.LlamaForCausalLM)(M.AttributeDict(cfg), w)
+    model.set_decode_graph(graph)
+    B, S0, dec = 2, 597, 4
+    ids = np.random.default_rng(11).integers(0, cfg.vocab_size, (B, S0 + dec))
+    wn, oc = O.to_numpy_f32(w), O.KVCache()
+    O.forward(cfg, wn, ids[:, :S0], oc)
+    cache = M.KVCache(max_tokens=1024)
+    model(ids[:, :S0], use_cache=True, kv_cache=cache, output_hidden_states=False)
+    for i in range(dec):
+        want = O.forward(cfg, wn, ids[:, S0 + i:S0 + i + 1], oc).logits
+        _, lg, _, _, _ = model(ids[:, S0 + i:S0 + i + 1], use_cache=True, kv_cache=cache, output_hidden_states=False)
+        check_close(lg.cpu().numpy(), want, f"{family} long-cache decode step {i} (graph={graph})")
+    assert cache.num_items() == S0 + dec
+
+
 def test_chunk_on_cache_raises_like_reference():
     meta, arr = load_golden("llama_tiny_chunk_on_cache")
     cfg = O.llama_config("tiny")
