@@ -52,6 +52,12 @@ typedef struct b2_config {
   int32_t precise;              /* 1: parity mode -- every bf16 activation is carried as hi+lo bf16 planes (exact weights,
                                    2x-K weight GEMMs, 3 MMAs per attention product): logits within 1e-2 of the
                                    reference at ~3x the cost; head_dim 64/128 only */
+  /* HF "llama3" RoPE frequency scaling (transformers modeling_rope_utils._compute_llama3_parameters); the reference
+   * never applies it (llama3.2_model_numpy.py:47 uses plain base^(-2i/HD)).  rope_factor <= 1 = off (reference). */
+  float rope_factor;                    /* Llama-3.2: 32 */
+  float rope_low_freq_factor;           /* Llama-3.2: 1 */
+  float rope_high_freq_factor;          /* Llama-3.2: 4 */
+  int32_t rope_original_max_positions;  /* Llama-3.2: 8192 */
 } b2_config;
 
 typedef struct b2_engine b2_engine;

@@ -18,7 +18,8 @@ class B2Config(C.Structure):
                 ("rope_theta", C.c_float), ("rms_norm_eps", C.c_float), ("hidden_act", C.c_int32),
                 ("gemma", C.c_int32), ("final_logit_softcap", C.c_float), ("attn_logit_softcap", C.c_float),
                 ("sliding_window", C.c_int32), ("attn_scale", C.c_float), ("always_causal", C.c_int32),
-                ("precise", C.c_int32)]
+                ("precise", C.c_int32), ("rope_factor", C.c_float), ("rope_low_freq_factor", C.c_float),
+                ("rope_high_freq_factor", C.c_float), ("rope_original_max_positions", C.c_int32)]
 
 
 class B2Stats(C.Structure):

@@ -395,12 +395,27 @@ static int attn_decode(const bf16* q, int ldq, const bf16* kc, const bf16* vc, b
 
 // host-side RoPE tables mirroring the reference's fp32 arithmetic (llama3.2_model_numpy.py:42-60):
 // inv_freq = 1/(base^(2i/HD)) in fp32, angle = inv_freq*pos in fp32, cos/sin of that fp32 angle.
-static void rope_tables_host(int HD, float base, int max_pos, std::vector<float>& c, std::vector<float>& s) {
+// Optional HF "llama3" frequency scaling (transformers modeling_rope_utils._compute_llama3_parameters, fp32 like
+// there): long wavelengths divided by `factor`, a smooth blend in the medium band; factor <= 1 = off (reference).
+static void rope_tables_host(int HD, float base, int max_pos, std::vector<float>& c, std::vector<float>& s,
+                             float factor = 0.f, float low_ff = 1.f, float high_ff = 4.f, int old_ctx = 8192) {
   const int half = HD / 2;
   std::vector<float> inv(half);
   for (int i = 0; i < half; ++i) {
     const float e = static_cast<float>(2 * i) / static_cast<float>(HD);
     inv[i] = 1.0f / powf(base, e);
+  }
+  if (factor > 1.0f) {
+    const float oc = static_cast<float>(old_ctx);
+    const float low_wl = oc / low_ff, high_wl = oc / high_ff;
+    for (int i = 0; i < half; ++i) {
+      const float wl = 2.0f * 3.14159265358979323846f / inv[i];
+      const float scaled = (wl > low_wl) ? inv[i] / factor : inv[i];
+      const float smooth = (oc / wl - low_ff) / (high_ff - low_ff);
+      const float blended = (1.0f - smooth) * scaled / factor + smooth * scaled;
+      const bool medium = !(wl < high_wl) && !(wl > low_wl);
+      inv[i] = medium ? blended : scaled;
+    }
   }
   c.resize(static_cast<size_t>(max_pos) * half);
   s.resize(c.size());
@@ -608,7 +623,8 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
     }
   }
   std::vector<float> cs, sn;
-  rope_tables_host(c.head_dim, c.rope_theta, c.max_positions, cs, sn);
+  rope_tables_host(c.head_dim, c.rope_theta, c.max_positions, cs, sn, c.rope_factor, c.rope_low_freq_factor,
+                   c.rope_high_freq_factor, c.rope_original_max_positions);
   CK(cudaMalloc(&e->rope_cos, cs.size() * 4));
   CK(cudaMalloc(&e->rope_sin, sn.size() * 4));
   CK(cudaMemcpy(e->rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));

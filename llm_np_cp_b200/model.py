@@ -117,7 +117,8 @@ class _CausalLM:
 
     def __init__(self, config, weights_dict: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
                  max_positions: Optional[int] = None, *, attn_logit_softcapping=None, sliding_window=None,
-                 use_query_pre_attn_scalar: bool = False, always_causal: bool = False, precise: bool = False):
+                 use_query_pre_attn_scalar: bool = False, always_causal: bool = False, precise: bool = False,
+                 rope_scaling: Optional[dict] = None):
         self.config = config
         L = _lib.lib()
         if L.b2_device_count() == 0:
@@ -150,6 +151,16 @@ class _CausalLM:
         # parity mode: every bf16 activation is carried as hi + lo (3 tensor-core products per attention product,
         # 2x K in the weight GEMMs); meets 1e-2 max-abs vs the reference.  Never quote throughput from it.
         c.precise = 1 if precise else 0
+        # HF "llama3" rope frequency scaling (config.json: rope_scaling = {rope_type: llama3, factor, low_freq_factor,
+        # high_freq_factor, original_max_position_embeddings}); the reference ignores it, so it is opt-in here
+        if rope_scaling:
+            kind = rope_scaling.get("rope_type", rope_scaling.get("type", "llama3"))
+            if kind != "llama3":
+                raise ValueError(f"rope_scaling type {kind!r} is not supported (llama3 only)")
+            c.rope_factor = float(rope_scaling["factor"])
+            c.rope_low_freq_factor = float(rope_scaling.get("low_freq_factor", 1.0))
+            c.rope_high_freq_factor = float(rope_scaling.get("high_freq_factor", 4.0))
+            c.rope_original_max_positions = int(rope_scaling.get("original_max_position_embeddings", 8192))
         self._cfg = c
         self.device = torch.device("cuda", device)
         self.vocab_size = c.vocab_size
@@ -356,9 +367,11 @@ def load_sharded_safetensors_via_weight_map(model_dir, index_filename="model.saf
     return all_tensors, config
 
 
-def load_model(model_name, device: int = 0):
+def load_model(model_name, device: int = 0, hf_faithful: bool = False):
     """load_model (llama3.2_model_numpy.py:1030-1047).  ``model_name`` is a local snapshot directory
-    (there is no network here); a hub id is resolved through huggingface_hub when one is reachable."""
+    (there is no network here); a hub id is resolved through huggingface_hub when one is reachable.
+    ``hf_faithful=True`` additionally applies what transformers does and the reference does not: the checkpoint's
+    llama3 ``rope_scaling``, a causal mask for every q_len, Gemma-2's attention soft-cap / sliding window."""
     global weights
     from transformers import AutoTokenizer
     model_dir = model_name
@@ -370,5 +383,12 @@ def load_model(model_name, device: int = 0):
     if "head_dim" not in config:
         config["head_dim"] = config["hidden_size"] // config["num_attention_heads"]
     is_gemma = "gemma" in str(config.get("model_type", "")).lower()
-    model = (Gemma2ForCausalLM if is_gemma else LlamaForCausalLM)(config, weights, device=device)
+    kw = {}
+    if hf_faithful:
+        if is_gemma:
+            kw["hf_flags"] = True
+        else:
+            kw["always_causal"] = True
+            kw["rope_scaling"] = config.get("rope_scaling") or None
+    model = (Gemma2ForCausalLM if is_gemma else LlamaForCausalLM)(config, weights, device=device, **kw)
     return tokenizer, model, config

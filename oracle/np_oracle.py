@@ -165,10 +165,29 @@ def rms_norm(x, gamma, eps, plus_one: bool = False):
     return n * g
 
 
-def rope_tables(head_dim: int, base: float, position_ids, dtype):
-    """cos/sin [1,S,HD] from plain RoPE -- no llama3 frequency scaling
+def llama3_scaled_inv_freq(inv_freq, rope_scaling):
+    """HF "llama3" RoPE frequency scaling, fp32 like transformers' modeling_rope_utils._compute_llama3_parameters
+    (the reference never applies it; this is an Extras option pinned against transformers in
+    tests/test_oracle_golden.py)."""
+    f32 = np.float32
+    factor, low_ff = f32(rope_scaling["factor"]), f32(rope_scaling.get("low_freq_factor", 1.0))
+    high_ff = f32(rope_scaling.get("high_freq_factor", 4.0))
+    old = f32(rope_scaling.get("original_max_position_embeddings", 8192))
+    inv_freq = inv_freq.astype(f32)
+    wavelen = f32(2 * np.pi) / inv_freq
+    scaled = np.where(wavelen > old / low_ff, inv_freq / factor, inv_freq).astype(f32)
+    smooth = ((old / wavelen - low_ff) / (high_ff - low_ff)).astype(f32)
+    blended = ((f32(1) - smooth) * scaled / factor + smooth * scaled).astype(f32)
+    medium = ~(wavelen < old / high_ff) & ~(wavelen > old / low_ff)
+    return np.where(medium, blended, scaled).astype(f32)
+
+
+def rope_tables(head_dim: int, base: float, position_ids, dtype, rope_scaling=None):
+    """cos/sin [1,S,HD] from plain RoPE -- no llama3 frequency scaling unless the Extras option asks for it
     (llama3.2_model_numpy.py:42-60).  inv_freq and the angle product are fp32."""
     inv_freq = 1.0 / (base ** (np.arange(0, head_dim, 2).astype(np.float32) / head_dim))
+    if rope_scaling:
+        inv_freq = llama3_scaled_inv_freq(inv_freq, rope_scaling)
     inv = np.expand_dims(np.expand_dims(inv_freq, 0).astype(np.float32), -1)
     inv = inv.repeat(position_ids.shape[0], axis=0)
     pos = np.expand_dims(position_ids, 1).astype(np.float32)
@@ -264,6 +283,7 @@ class Extras:
     sliding_layers: str = "even"               # HF default pattern: even layers slide
     attn_scale: Optional[float] = None         # e.g. query_pre_attn_scalar ** -0.5
     always_causal: bool = False                # drop the q_len > 2 quirk
+    rope_scaling: Optional[dict] = None        # HF llama3 frequency scaling {factor, low_freq_factor, high_freq_factor, original_max_position_embeddings}
 
 
 def attention(cfg, W, li, x, cos, sin, cache, faithful, stable_softmax, ex: Extras):
@@ -344,14 +364,14 @@ def forward(cfg, W: Dict[str, np.ndarray], input_ids, cache: Optional[KVCache] =
     hs, att = [], []
     cos = sin = None
     if not gem:
-        cos, sin = rope_tables(cfg.head_dim, cfg.rope_theta, pos, x.dtype)  # once per forward (:682)
+        cos, sin = rope_tables(cfg.head_dim, cfg.rope_theta, pos, x.dtype, ex.rope_scaling)  # once per forward (:682)
     for li in range(cfg.num_hidden_layers):
         hs.append(x)
         p = f"model.layers.{li}."
         if gem:
             # cos/sin are recomputed per layer in the activations' dtype (gemma2_model.py:506)
             h = rms_norm(x, W[p + "input_layernorm.weight"], cfg.rms_norm_eps, True)
-            cos, sin = rope_tables(cfg.head_dim, cfg.rope_theta, pos, h.dtype)
+            cos, sin = rope_tables(cfg.head_dim, cfg.rope_theta, pos, h.dtype, ex.rope_scaling)
             a, pr = attention(cfg, W, li, h, cos, sin, cache, faithful, True, ex)
             x = x + rms_norm(a, W[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps, True)
             h = rms_norm(x, W[p + "pre_feedforward_layernorm.weight"], cfg.rms_norm_eps, True)

@@ -111,6 +111,33 @@ def test_decode_long_cache_vs_oracle(family, graph):
     assert cache.num_items() == S0 + dec
 
 
+def test_hf_faithful_llama_vs_transformers_golden():
+    """HF-faithful options the reference lacks (llama3 rope scaling, causal mask for every q_len, chunked prefill on a
+    non-empty cache) against outputs of transformers' LlamaForCausalLM (tests/golden/hf_llama_tiny_rope3.npz)."""
+    meta, arr = load_golden("hf_llama_tiny_rope3")
+    cfg, w, model = build(meta, always_causal=True, rope_scaling=meta["rope_scaling"])
+    S, dec = meta["S"], meta["decode_steps"]
+    cache = M.KVCache(max_tokens=256)
+    _, logits, _, hs, _ = model(arr["ids"][:, :S], use_cache=True, kv_cache=cache)
+    check_close(logits.cpu().numpy(), arr["logits"], "hf llama3-rope prefill logits")
+    for i, h in enumerate(hs):
+        check_close(h.cpu().numpy(), arr["hidden"][i], f"hf llama3-rope hidden[{i}]")
+    for i in range(dec):
+        _, lg, _, _, _ = model(arr["ids"][:, S + i:S + i + 1], use_cache=True, kv_cache=cache)
+        check_close(lg.cpu().numpy(), arr["decode_logits"][i], f"hf llama3-rope decode step {i}")
+    _, q2, _, _, _ = model(arr["ids"][:, :2], use_cache=False)
+    check_close(q2.cpu().numpy(), arr["qlen2_logits"], "hf q_len=2 (masked, unlike the reference)")
+    # chunked prefill: 100 tokens, then 50 more on the non-empty cache (the reference raises here)
+    cache2 = M.KVCache(max_tokens=256)
+    model(arr["ids"][:, :100], use_cache=True, kv_cache=cache2, output_hidden_states=False)
+    _, lg2, _, _, _ = model(arr["ids"][:, 100:S], use_cache=True, kv_cache=cache2, output_hidden_states=False)
+    check_close(lg2.cpu().numpy(), arr["logits"][:, 100:S], "hf chunked prefill (second chunk)")
+    # without the option the engine reproduces the reference, not HF
+    _, _, plain = build(meta)
+    _, lp, _, _, _ = plain(arr["ids"][:, :S], use_cache=False)
+    assert np.abs(lp.cpu().numpy() - arr["logits"]).max() > 0.15 * arr["logits"].std()
+
+
 def test_chunk_on_cache_raises_like_reference():
     meta, arr = load_golden("llama_tiny_chunk_on_cache")
     cfg = O.llama_config("tiny")
