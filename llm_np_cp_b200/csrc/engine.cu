@@ -561,11 +561,14 @@ static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* 
     lda *= 2;
   }
   if (!a_rows) a_rows = e->ws_tokens > p.M ? e->ws_tokens : p.M;
-  CKR(get_tmap(e, a, a_rows, p.K, lda, GEMM_BM, &ta));
   // prefill-size GEMMs run on CTA pairs (cta_group::2, 256 x 256 tiles): measured 1420 vs 1300 TFLOP/s in-step for the
   // 1-CTA kernel (B2_GEMM1=1 selects the latter)
   static const bool use2 = getenv("B2_GEMM1") == nullptr;
   const bool two_cta = use2 && bn == 256 && p.split_k == 1 && p.N % 256 == 0;
+  // few-row GEMMs (decode): the A box covers only the rows that exist (32 / 64) -- A is 2/3 of the TMA bytes of a
+  // BN = 64 weight-streaming CTA otherwise
+  p.a_box_rows = (!two_cta && p.M <= 64) ? (p.M <= 32 ? 32 : 64) : 0;
+  CKR(get_tmap(e, a, a_rows, p.K, lda, p.a_box_rows ? p.a_box_rows : GEMM_BM, &ta));
   CKR(get_tmap(e, w, p.N, p.k_wrap, p.k_wrap, two_cta ? 128 : bn, &tb));
   tc = ta;
   if (epi == EPI_F32 || epi == EPI_RESID) CKR(get_tmap(e, p.out, c_rows ? c_rows : p.M, p.N, p.ldo, 32, &tc, true));
@@ -1289,9 +1292,10 @@ extern "C" int b2_op_gemm(const void* a, const void* w, void* out, int M, int N,
   if (epi == EPI_QKV_ROPE) return fail(B2_ERR_ARG, "use b2_op_qkv_rope");
   CUtensorMap ta, tb;
   const bool two_cta = bn == 512;                     // test hook: bn = 512 selects the 2-CTA kernel (256-wide tiles)
-  CKR(make_tmap(&ta, a, M, K, K, GEMM_BM));
-  CKR(make_tmap(&tb, w, N, K, K, two_cta ? 128 : bn));
   GemmParams p = base_params(M, N, K);
+  p.a_box_rows = (!two_cta && M <= 64) ? (M <= 32 ? 32 : 64) : 0;     // same rule as eng_gemm
+  CKR(make_tmap(&ta, a, M, K, K, p.a_box_rows ? p.a_box_rows : GEMM_BM));
+  CKR(make_tmap(&tb, w, N, K, K, two_cta ? 128 : bn));
   p.split_k = split_k < 1 ? 1 : split_k;
   p.out = out;
   p.ldo = (epi == EPI_GLU) ? N / 2 : N;

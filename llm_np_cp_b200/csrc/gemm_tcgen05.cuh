@@ -49,6 +49,8 @@ struct GemmParams {
   const float* rope_cos;   // [max_pos][HD/2]
   const float* rope_sin;
   int kv_lo_off;           // precise mode: element offset of the lo plane of the caches (0 = none)
+  int a_box_rows;          // 1-CTA kernel: rows of A one TMA box brings in (32/64 when M is that small, else 0 = 128);
+                           // the remaining rows of the 128-row MMA tile are zeroed once instead of fetched every k-step
 };
 
 constexpr int GEMM_BM = 128;
@@ -303,6 +305,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  const int a_rows_box = p.a_box_rows > 0 ? p.a_box_rows : GEMM_BM;
+  const uint32_t a_tx = static_cast<uint32_t>(a_rows_box) * 128u;       // bytes of A per ring slot actually loaded
+  if (a_rows_box < GEMM_BM) {                  // few-row GEMM (decode): rows the box does not cover stay zero
+    const int tail16 = (GEMM_BM - a_rows_box) * 8;                       // 16-byte chunks per slot
+    for (int i = threadIdx.x; i < STAGES * tail16; i += GEMM_THREADS) {
+      const int s = i / tail16, c = i - s * tail16;
+      *reinterpret_cast<uint4*>(sA + s * Cfg::A_BYTES + a_rows_box * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
@@ -333,7 +345,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tile_coords(blockIdx.x, mb, nb, kb0);
         pre = KB < STAGES ? KB : STAGES;
         for (int kb = 0; kb < pre; ++kb) {
-          mbar_expect_tx(&full[kb], Cfg::A_BYTES + Cfg::B_BYTES);
+          mbar_expect_tx(&full[kb], a_tx + Cfg::B_BYTES);
           const int ka = (kb0 + kb) * GEMM_BK;
           const int kw = ka >= p.k_wrap ? ka - p.k_wrap : ka;
           tma_load_2d(sB + kb * Cfg::B_BYTES, &tmap_b, &full[kb], kw, nb * BN, kEvictNormal);
@@ -351,7 +363,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_a, &full[stage], ka, mb * GEMM_BM, kEvictNormal);
           } else {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+            mbar_expect_tx(&full[stage], a_tx + Cfg::B_BYTES);
             tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_a, &full[stage], ka, mb * GEMM_BM, kEvictNormal);
             tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_b, &full[stage], kw, nb * BN, kEvictNormal);
           }

@@ -27,6 +27,7 @@ def test_rmsnorm(M, H):
 GEMM_SHAPES = [
     (128, 256, 64), (128, 256, 256), (256, 512, 2048), (100, 256, 128), (1000, 768, 512),
     (2048, 3072, 2048), (333, 2304, 2304),
+    (64, 512, 2048), (40, 256, 512), (32, 256, 256), (7, 256, 1024), (1, 512, 128),   # few-row path: 64- / 32-row A boxes
 ]
 
 
