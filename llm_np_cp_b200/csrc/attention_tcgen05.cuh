@@ -157,12 +157,11 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
 // S lives at tS_row, O at tO_row (TMEM, this thread's lane), P goes to sP (smem, 128B-swizzled rows).
 template <int SCH, bool MASK, bool CAP>
 __device__ __forceinline__ float att_exp_regs(uint32_t (&x)[SCH][32], uint8_t* sP, int r, float sl2, float m_safe,
-                                              float cap_in, float cap_out, int lo, unsigned span, uint8_t* sPlo,
-                                              int c_off = 0) {
+                                              float cap_in, float cap_out, int lo, unsigned span, uint8_t* sPlo) {
   float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < SCH; ++c)
-    att_exp32<MASK, CAP>(x[c], c_off + c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum, sPlo);
+    att_exp32<MASK, CAP>(x[c], c, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sum, sPlo);
   return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
@@ -170,12 +169,7 @@ template <int SCH, int OCH>
 __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_row, uint8_t* sP, int r, bool need_mask,
                                                  int lo, unsigned span, bool cap, float sl2, float cap_in, float cap_out,
                                                  float& m_used, float& l, bool have_o, uint64_t* bar_o, uint32_t o_parity,
-                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr, AttTrace* tr = nullptr,
-                                                 int c_off = 0, float* mx_mine = nullptr, const float* mx_other = nullptr,
-                                                 int pair_bar = 0) {
-  // c_off / mx_* / pair_bar: split-row mode -- this thread owns only chunks [c_off, c_off + SCH) of the row (tS_row,
-  // tO_row already point at its columns); the row max is exchanged with the partner thread (other warp, same TMEM
-  // lanes) through shared memory + a 64-thread named barrier so both use the same scale.
+                                                 uint64_t* bar_sfree, uint8_t* sPlo = nullptr, AttTrace* tr = nullptr) {
   constexpr float TAU = 8.0f;   // lazy-rescale threshold (log2 units): P stays <= 2^8
   uint32_t x[SCH][32];
 #pragma unroll
@@ -189,17 +183,12 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
   float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   if (need_mask) {
 #pragma unroll
-    for (int c = 0; c < SCH; ++c) att_max32<true>(x[c], (c_off + c) * 32 - lo, span, m);
+    for (int c = 0; c < SCH; ++c) att_max32<true>(x[c], c * 32 - lo, span, m);
   } else {
 #pragma unroll
     for (int c = 0; c < SCH; ++c) att_max32<false>(x[c], 0, 0u, m);
   }
-  float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-  if (mx_mine) {
-    *mx_mine = mx;
-    named_bar_sync(pair_bar, 64);
-    mx = fmaxf(mx, *mx_other);
-  }
+  const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
   float m_tile = mx;                               // -> log2 domain, after the optional soft-cap
   if (mx != -INFINITY) m_tile = cap ? cap_out * fast_tanh(mx * cap_in) : mx * sl2;
   float alpha = 1.0f;
@@ -229,11 +218,11 @@ __device__ __forceinline__ void att_softmax_tile(uint32_t tS_row, uint32_t tO_ro
   const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
   float lsum;
   if (cap) {
-    lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off)
-                     : att_exp_regs<SCH, false, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off);
+    lsum = need_mask ? att_exp_regs<SCH, true, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo)
+                     : att_exp_regs<SCH, false, true>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo);
   } else {
-    lsum = need_mask ? att_exp_regs<SCH, true, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off)
-                     : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo, c_off);
+    lsum = need_mask ? att_exp_regs<SCH, true, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo)
+                     : att_exp_regs<SCH, false, false>(x, sP, r, sl2, m_safe, cap_in, cap_out, lo, span, sPlo);
   }
   l += lsum;
   if (tr) tr->ev(37);
@@ -495,325 +484,6 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Pipelined prefill kernel (head_dim 64 / 128): one CTA owns TWO consecutive 128-row q tiles of one
-// (batch, head) and ping-pongs them through the tensor core.  1 CTA / SM, 384 threads = 3 warpgroups:
-//   warps 0-3   softmax / correction / epilogue of q tile 0        (thread = q row = TMEM lane)
-//   warps 4-7   same for q tile 1
-//   warp  8     TMA producer: both Q tiles once, K/V tiles through a 3-stage ring (shared by both q tiles)
-//   warp  9     tcgen05.mma issuer (warps 10-11 idle; they only complete the third warpgroup)
-// Register budget is moved with setmaxnreg: the softmax warpgroups hold a whole S row (128 fp32) in registers
-// so TMEM is read once per score; the producer/MMA warpgroup gives its registers away.
-// Per kv tile j and q tile g the MMA warp issues, in this order:
-//     wait S_g(j) consumed  -> S_g(j+1) = Q_g.K_(j+1)^T        (for g = 0, 1)
-//     wait P_g(j) written   -> O_g     += P_g(j).V_j           (for g = 0, 1)
-// so the next scores are already in TMEM when a q tile's softmax warps finish the current ones, and P.V of
-// one q tile overlaps the exponentials of the other.
-// TMEM: S0 | S1 | O0 | O1  (2*BNKV + 2*HD <= 512 columns).
-// ---------------------------------------------------------------------------------------------
-// SPLIT = softmax threads per q row: 1 (8 softmax warps, whole row in registers) or 2 (16 softmax warps, each thread
-// owns half of the kv columns of its row and half of the O columns; 4 warps per scheduler hide the in-order MUFU /
-// dependency stalls of the exponential phase)
-template <int SPLIT>
-constexpr int att2_threads() { return 32 * (8 * SPLIT + 4); }
-
-
-template <int HD>
-struct Attn2Cfg {
-  static constexpr int BNKV = (HD == 64) ? 128 : 64;
-  static constexpr int KV_STAGES = 3;
-  static constexpr int Q_BYTES = ATT_BM * HD * 2;        // one q tile
-  static constexpr int KV_BYTES = BNKV * HD * 2;         // one K or V tile
-  static constexpr int P_BYTES = ATT_BM * BNKV * 2;      // one P tile
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int EX_BYTES = 8192;                  // row-max / row-sum exchange between the two threads of a row
-  static constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + BAR_BYTES + EX_BYTES + 1024;
-  static constexpr int TMEM_COLS = 512;
-  static_assert(2 * BNKV + 2 * HD <= 512, "TMEM budget");
-};
-
-template <int HD, int SPLIT>
-__global__ void __launch_bounds__(att2_threads<SPLIT>(), 1)
-attn_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                         const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using Cfg = Attn2Cfg<HD>;
-  constexpr int BNKV = Cfg::BNKV;
-  constexpr int ST = Cfg::KV_STAGES;
-  constexpr int HB = HD / 64;
-  constexpr int SCH = BNKV / 32;
-  constexpr int OCH = HD / 32;
-  constexpr int SMW = 8 * SPLIT;                       // softmax warps; warp SMW = TMA producer, SMW + 1 = MMA issuer
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                                   // [2][128 x HD]
-  uint8_t* sK = sQ + 2 * Cfg::Q_BYTES;                  // [ST]
-  uint8_t* sV = sK + ST * Cfg::KV_BYTES;                // [ST]
-  uint8_t* sP = sV + ST * Cfg::KV_BYTES;                // [2][128 x BNKV]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
-  uint64_t* bar_q = bars;            // 1
-  uint64_t* k_full = bars + 1;       // [ST]
-  uint64_t* v_full = bars + 4;       // [ST]
-  uint64_t* kv_empty = bars + 7;     // [ST]
-  uint64_t* s_full = bars + 10;      // [2]  S_g written by the tensor core
-  uint64_t* s_free = bars + 12;      // [2]  S_g copied to registers by all 128 softmax threads
-  uint64_t* p_ready = bars + 14;     // [2]  P_g written to smem by all 128 softmax threads
-  uint64_t* o_done = bars + 16;      // [2]  O_g += P_g.V finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  float* ex = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [2 g][128 rows][2 halves][4]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long cta_t0 = 0;
-  if (p.cta_trace && threadIdx.x == 0) cta_t0 = globaltimer_ns();
-  const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
-  const int n_pairs = (n_qt + 1) / 2;
-  const int pi = n_pairs - 1 - static_cast<int>(blockIdx.x);    // heaviest pairs first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int kvh = h / (p.NH / p.NKV);
-
-  if (warp == SMW && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1);
-      mbar_init(&s_free[g], 128 * SPLIT);
-      mbar_init(&p_ready[g], 128 * SPLIT);
-      mbar_init(&o_done[g], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == SMW + 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  pdl_trigger();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                               // Q/K/V and the cache length come from the preceding kernels
-  const int t0 = *p.t0_ptr;
-  const int T = t0 + p.S;
-  // per q tile g: rows [q0g, q0g+128), kv tiles [jb[g], je[g])
-  int q0g[2], jb[2], je[2];
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    q0g[g] = (2 * pi + g) * ATT_BM;
-    if (2 * pi + g >= n_qt) {
-      jb[g] = je[g] = 0;          // tile does not exist (odd tile count)
-    } else {
-      int kv_end = T;
-      if (p.causal) kv_end = min(T, t0 + q0g[g] + ATT_BM);
-      int kv_begin = 0;
-      if (p.window > 0) kv_begin = max(0, t0 + q0g[g] - p.window + 1);
-      jb[g] = kv_begin / BNKV;
-      je[g] = (kv_end + BNKV - 1) / BNKV;
-    }
-  }
-  const int j_lo = (je[1] > jb[1]) ? min(jb[0], jb[1]) : jb[0];
-  const int j_hi = max(je[0], je[1]);
-
-  if (warp >= SMW) {
-    setmaxnreg_dec<40>();
-    if (warp == SMW) {
-      // ------------------------------ TMA producer ------------------------------
-      if (elect_one()) {
-        mbar_expect_tx(bar_q, 2 * Cfg::Q_BYTES);
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-#pragma unroll
-          for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(sQ + g * Cfg::Q_BYTES + hb * (ATT_BM * 128), &tmap_q, bar_q, h * HD + hb * 64,
-                        b * p.S + q0g[g], kEvictFirst);
-        const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int j = j_lo; j < j_hi; ++j) {
-          mbar_wait(&kv_empty[stage], phase ^ 1);
-          mbar_expect_tx(&k_full[stage], Cfg::KV_BYTES);
-#pragma unroll
-          for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(sK + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[stage], hb * 64,
-                        kv_row0 + j * BNKV, kEvictLast);
-          mbar_expect_tx(&v_full[stage], Cfg::KV_BYTES);
-#pragma unroll
-          for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(sV + stage * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_v, &v_full[stage], hb * 64,
-                        kv_row0 + j * BNKV, kEvictLast);
-          if (++stage == ST) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    } else if (warp == SMW + 1) {
-      // ------------------------------ MMA issuer ------------------------------
-      if (elect_one()) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
-        constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // P (K-major) x V (MN-major)
-        auto issue_s = [&](int g, int stage) {    // S_g = Q_g . K^T
-          const uint32_t q_addr = smem_u32(sQ + g * Cfg::Q_BYTES);
-          const uint32_t k_addr = smem_u32(sK + stage * Cfg::KV_BYTES);
-#pragma unroll
-          for (int hb = 0; hb < HB; ++hb)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_base + g * BNKV, umma_smem_desc(q_addr + hb * (ATT_BM * 128) + k * 32, 16, 1024),
-                           umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024), idesc_s, (hb | k) != 0 ? 1u : 0u);
-          umma_commit(&s_full[g]);
-        };
-        auto issue_pv = [&](int g, int stage, bool first) {   // O_g (+)= P_g . V
-          const uint32_t p_addr = smem_u32(sP + g * Cfg::P_BYTES);
-          const uint32_t v_addr = smem_u32(sV + stage * Cfg::KV_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < BNKV / 16; ++kk)
-            umma_bf16_ss(tmem_base + 2 * BNKV + g * HD,
-                         umma_smem_desc(p_addr + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
-                         umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (!first || kk != 0) ? 1u : 0u);
-          umma_commit(&o_done[g]);
-        };
-        AttTrace tr;
-        tr.init(p.trace, 0);
-        tr.ev(0);
-        mbar_wait(bar_q, 0);
-        tr.ev(1);
-        auto has = [&](int g, int j) { return j >= jb[g] && j < je[g]; };
-        auto st_of = [&](int j) { return (j - j_lo) % ST; };
-        auto ph_of = [&](int j) { return static_cast<uint32_t>(((j - j_lo) / ST) & 1); };
-        if (j_lo < j_hi) {
-          mbar_wait(&k_full[0], 0);
-          tc_fence_after();
-#pragma unroll
-          for (int g = 0; g < 2; ++g)
-            if (has(g, j_lo)) issue_s(g, 0);
-        }
-        // Skewed schedule: q tile 1 runs half an iteration behind q tile 0, so the exponentials (MUFU) of one tile
-        // overlap the TMEM loads / row max / waits of the other instead of both fighting for the XU pipe at once.
-        //   per kv tile j:  S0(j+1) | PV1(j-1) | S1(j+1) | PV0(j)
-        for (int j = j_lo; j <= j_hi; ++j) {
-          // (1) q tile 0: next scores as soon as the current ones are in registers
-          if (has(0, j + 1)) {
-            if (has(0, j)) mbar_wait(&s_free[0], (j - jb[0]) & 1);
-            tr.ev(10);
-            mbar_wait(&k_full[st_of(j + 1)], ph_of(j + 1));
-            tr.ev(12);
-            tc_fence_after();
-            issue_s(0, st_of(j + 1));
-          }
-          // (2) q tile 1: P.V of the previous kv tile; it is the last reader of that ring slot
-          if (j > j_lo && has(1, j - 1)) {
-            mbar_wait(&p_ready[1], (j - 1 - jb[1]) & 1);
-            tr.ev(21);
-            mbar_wait(&v_full[st_of(j - 1)], ph_of(j - 1));
-            tc_fence_after();
-            issue_pv(1, st_of(j - 1), j - 1 == jb[1]);
-            tr.ev(23);
-            umma_commit(&kv_empty[st_of(j - 1)]);
-          }
-          if (j == j_hi) break;
-          // (3) q tile 1: next scores
-          if (has(1, j + 1)) {
-            if (has(1, j)) mbar_wait(&s_free[1], (j - jb[1]) & 1);
-            tr.ev(11);
-            mbar_wait(&k_full[st_of(j + 1)], ph_of(j + 1));
-            tr.ev(13);
-            tc_fence_after();
-            issue_s(1, st_of(j + 1));
-          }
-          // (4) q tile 0: P.V of this kv tile
-          if (has(0, j)) {
-            mbar_wait(&p_ready[0], (j - jb[0]) & 1);
-            tr.ev(20);
-            mbar_wait(&v_full[st_of(j)], ph_of(j));
-            tc_fence_after();
-            issue_pv(0, st_of(j), j == jb[0]);
-            tr.ev(22);
-            if (!has(1, j)) umma_commit(&kv_empty[st_of(j)]);   // q tile 1 does not read this kv tile
-          }
-        }
-      }
-    }
-  } else {
-    // ------------------------------ softmax / correction / epilogue (8 warps, 2 q tiles) ------------------------------
-    setmaxnreg_inc<(SPLIT == 1) ? 232 : 104>();
-    const int g = (warp >> 2) & 1;                   // q tile of this warp
-    const int half = warp >> 3;                      // which half of the row's columns (SPLIT == 2), else 0
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;               // row inside the tile == TMEM lane
-    constexpr int SCHL = SCH / SPLIT, OCHL = OCH / SPLIT;   // chunks of S / of O owned by this thread
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS_row = tmem_base + g * BNKV + half * (SCHL * 32) + lane_off;
-    const uint32_t tO_row = tmem_base + 2 * BNKV + g * HD + half * (OCHL * 32) + lane_off;
-    uint8_t* sPg = sP + g * Cfg::P_BYTES;
-    float* exr = ex + ((g * 128 + r) * 2) * 4;       // this row's exchange slots: [half][0,1 = max by tile parity, 2 = l]
-    const int pair_bar = 1 + g * 4 + quarter;        // named barrier shared by the two warps of this (q tile, quarter)
-    const int q0 = q0g[g];
-    const int qpos = t0 + q0 + r;
-    const float LOG2E = 1.4426950408889634f;
-    const float sl2 = p.scale * LOG2E;
-    const bool cap = p.softcap > 0.f;
-    const float cap_in = cap ? p.scale / p.softcap : 0.f, cap_out = p.softcap * LOG2E;
-    float m_used = -INFINITY, l = 0.f;
-    const int n_tiles = je[g] - jb[g];
-    AttTrace tr;
-    tr.init((quarter == 0 && half == 0 && lane == 0) ? p.trace : nullptr, 1 + g);
-    for (int it = 0; it < n_tiles; ++it) {
-      const int kv0 = (jb[g] + it) * BNKV;
-      const bool need_mask = (p.causal && kv0 + BNKV - 1 > t0 + q0) || (kv0 + BNKV > T) ||
-                             (p.window > 0 && kv0 < t0 + q0 + ATT_BM - p.window);
-      int lo = 0, hi = BNKV;
-      if (need_mask) {
-        int last = T - 1;
-        if (p.causal) last = min(last, qpos);
-        hi = min(BNKV, last - kv0 + 1);
-        if (p.window > 0) lo = max(0, qpos - p.window + 1 - kv0);
-      }
-      const unsigned span = hi > lo ? static_cast<unsigned>(hi - lo) : 0u;
-      tr.ev(30);
-      mbar_wait(&s_full[g], it & 1);
-      tr.ev(31);
-      tc_fence_after();
-      att_softmax_tile<SCHL, OCHL>(tS_row, tO_row, sPg, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l, it > 0,
-                                   &o_done[g], (it - 1) & 1, &s_free[g], nullptr, &tr, half * SCHL,
-                                   SPLIT == 2 ? exr + half * 4 + (it & 1) : nullptr, exr + (1 - half) * 4 + (it & 1), pair_bar);
-      fence_proxy_async_smem();
-      tr.ev(38);
-      tc_fence_before();
-      mbar_arrive(&p_ready[g]);
-      tr.ev(35);
-    }
-    if (n_tiles > 0) {
-      mbar_wait(&o_done[g], (n_tiles - 1) & 1);
-      tc_fence_after();
-    }
-    if (SPLIT == 2) {                                // row sum = sum of the two halves (same scale m_used in both)
-      exr[half * 4 + 2] = l;
-      named_bar_sync(pair_bar, 64);
-      l += exr[(1 - half) * 4 + 2];
-    }
-    if (2 * pi + g < n_qt)
-      att_store_out<OCHL>(tO_row, n_tiles > 0, l, (q0 + r) < p.S,
-                          p.out + static_cast<size_t>(b * p.S + q0 + r) * p.ldo + h * HD + half * (OCHL * 32));
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == SMW + 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-  if (p.cta_trace && threadIdx.x == 0) {
-    unsigned long long* t = p.cta_trace + 4 * ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
-    t[0] = cta_t0;
-    t[1] = globaltimer_ns();
-    t[2] = smid();
-    t[3] = static_cast<unsigned long long>(clock64());
   }
 }
 

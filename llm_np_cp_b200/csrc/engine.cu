@@ -261,23 +261,6 @@ static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return B2_OK;
 }
 
-template <int HD, int SPLIT>
-static int launch_attn_pair_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
-                              cudaStream_t st) {
-  auto kern = attn_prefill_pair_kernel<HD, SPLIT>;
-  static bool attr[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 16 || !attr[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<HD>::SMEM_BYTES));
-    if (dev < 16) attr[dev] = true;
-  }
-  const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
-  dim3 grid((n_qt + 1) / 2, p.NH, p.B);
-  CK(launch_k(kern, grid, dim3(att2_threads<SPLIT>()), Attn2Cfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
-  return B2_OK;
-}
-
 template <int HD>
 static int launch_attn_co_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                             cudaStream_t st) {
@@ -295,8 +278,9 @@ static int launch_attn_co_t(const CUtensorMap& tq, const CUtensorMap& tk, const 
   return B2_OK;
 }
 
-// prefill attention dispatch: the pipelined two-q-tile kernel for head_dim 64/128 (unless B2_ATTN_SINGLE is set
-// or the sequence fits one q tile), the single-tile kernel otherwise (head_dim 256: TMEM/smem budget).
+// prefill attention dispatch: the co-resident kernel (one q tile per CTA, two CTAs per SM) for head_dim 64/128 unless
+// B2_ATTN_SINGLE is set or the sequence fits one q tile; the one-CTA-per-SM single-tile kernel otherwise (head_dim 256:
+// TMEM/smem budget; precise mode: three MMAs per product).
 static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, const AttnParams& p_in, int HD,
                         cudaStream_t st) {
   CUtensorMap tq, tk, tv;
@@ -307,10 +291,10 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
   if (const char* ev = getenv("B2_ATT_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(ev, nullptr, 0));   // device pointer (diagnostics)
   static const bool force_single = getenv("B2_ATTN_SINGLE") != nullptr;
   const bool precise = p.q_lo_col != 0;
-  const bool pair = !precise && !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
+  const bool co = !precise && !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
   const int planes = precise ? 2 : 1;
   const uint64_t kv_rows = static_cast<uint64_t>(planes) * (precise ? p.kv_lo_row : static_cast<uint64_t>(p.B) * p.NKV * p.Tmax);
-  const int bnkv = precise ? 64 : (pair ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64));
+  const int bnkv = precise ? 64 : (co ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64));
   CKR(make_tmap(&tq, q, static_cast<uint64_t>(p.B) * p.S, static_cast<uint64_t>(planes) * p.NH * HD, ldq, ATT_BM));
   CKR(make_tmap(&tk, kc, kv_rows, HD, HD, bnkv));
   CKR(make_tmap(&tv, vc, kv_rows, HD, HD, bnkv));
@@ -319,13 +303,7 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
     if (HD == 128) return launch_attn_t<128, 2>(tq, tk, tv, p, st);
     return fail(B2_ERR_ARG, "precise mode supports head_dim 64 and 128 only");
   }
-  static const bool use_co = getenv("B2_ATTN_PAIR") == nullptr;   // default: one q tile per CTA, two CTAs per SM
-  if (pair && use_co) return HD == 64 ? launch_attn_co_t<64>(tq, tk, tv, p, st) : launch_attn_co_t<128>(tq, tk, tv, p, st);
-  if (pair) {
-    static const int split = getenv("B2_ATTN_SPLIT") ? atoi(getenv("B2_ATTN_SPLIT")) : 1;   // softmax threads per q row (2 measured slower: the XU pipe, not latency, bounds the exp phase)
-    if (split == 2) return HD == 64 ? launch_attn_pair_t<64, 2>(tq, tk, tv, p, st) : launch_attn_pair_t<128, 2>(tq, tk, tv, p, st);
-    return HD == 64 ? launch_attn_pair_t<64, 1>(tq, tk, tv, p, st) : launch_attn_pair_t<128, 1>(tq, tk, tv, p, st);
-  }
+  if (co) return HD == 64 ? launch_attn_co_t<64>(tq, tk, tv, p, st) : launch_attn_co_t<128>(tq, tk, tv, p, st);
   if (HD == 64) return launch_attn_t<64, 1>(tq, tk, tv, p, st);
   if (HD == 128) return launch_attn_t<128, 1>(tq, tk, tv, p, st);
   if (HD == 256) return launch_attn_t<256, 1>(tq, tk, tv, p, st);

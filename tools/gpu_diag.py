@@ -255,7 +255,7 @@ def stage_attn_cta():
         q = bf16_randn(B * S, NH * HD, seed=13)
         kc, vc = bf16_randn(B, NKV, S, HD, seed=14), bf16_randn(B, NKV, S, HD, seed=15)
         out = torch.zeros((B * S, NH * HD), dtype=torch.bfloat16, device="cuda")
-        npair = S // 128 if (not os.environ.get('B2_ATTN_PAIR')) else (S // 128 + 1) // 2
+        npair = S // 128                   # q tiles = blockIdx.x range (heaviest first)
         ncta = npair * NH * B
         tb = torch.zeros(ncta * 4, dtype=torch.int64, device="cuda")
         os.environ["B2_ATT_CTATRACE"] = hex(tb.data_ptr())
@@ -273,7 +273,7 @@ def stage_attn_cta():
         x = np.arange(ncta) % npair           # blockIdx.x (pair index reversed: 0 = heaviest)
         for bx in range(npair):
             d = dur[x == bx]
-            iters = (npair - bx) if (not os.environ.get('B2_ATTN_PAIR')) else 2 * (npair - 1 - bx) + 2
+            iters = npair - bx
             print(f"   blockIdx.x {bx:2d} ({iters:3d} kv iters): mean {d.mean() / 1e3:7.2f} us  min {d.min() / 1e3:7.2f}  max {d.max() / 1e3:7.2f}")
         gaps, busy, last_end, ghz = [], [], [], []
         for s_ in np.unique(sm):
