@@ -42,8 +42,10 @@ rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bf
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= M) return;
+  // rows are walked from the END of the residual stream: the GEMM in front of this kernel wrote x in ascending row
+  // order and x (134 MB at 16384 tokens) is about the size of L2, so its last rows are the ones still cached
+  const int row = M - 1 - (blockIdx.x * 8 + warp);
+  if (row < 0) return;
   const int nv = H >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * H);
   float4 v[NORM_MAXV];
