@@ -464,7 +464,7 @@ struct GraphKey {
 struct b2_engine {
   b2_config cfg;
   int device;
-  cudaStream_t stream;
+  cudaStream_t stream = nullptr;
   bool finalized = false;
   int q_cols, kv_cols, qkv_n;
   bf16* embed = nullptr;
@@ -559,29 +559,10 @@ static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* 
   return r;
 }
 
-extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** out) {
-  if (!cfg || !out) return fail(B2_ERR_ARG, "null argument");
-  CKR(require_gpu(device));
-  const b2_config& c = *cfg;
-  if (c.hidden_size % 128 || c.hidden_size > 128 * NORM_MAXV)
-    return fail(B2_ERR_ARG, "hidden_size %d must be a multiple of 128 and <= %d", c.hidden_size, 128 * NORM_MAXV);
-  if (c.head_dim != 64 && c.head_dim != 128 && c.head_dim != 256)
-    return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", c.head_dim);
-  if (c.num_key_value_heads <= 0 || c.num_attention_heads % c.num_key_value_heads)
-    return fail(B2_ERR_ARG, "num_attention_heads %d must be a multiple of num_key_value_heads %d",
-                c.num_attention_heads, c.num_key_value_heads);
-  // the reference raises ValueError on the same condition (llama3.2_model_numpy.py:361-365)
-  if (c.hidden_size % c.num_attention_heads)
-    return fail(B2_ERR_ARG, "hidden_size must be divisible by num_heads (got `hidden_size`: %d and `num_heads`: %d).",
-                c.hidden_size, c.num_attention_heads);
-  if (c.intermediate_size % 64) return fail(B2_ERR_ARG, "intermediate_size %d must be a multiple of 64", c.intermediate_size);
-  if (c.vocab_size % 32) return fail(B2_ERR_ARG, "vocab_size %d must be a multiple of 32", c.vocab_size);
-  if (c.max_positions <= 0) return fail(B2_ERR_ARG, "max_positions must be positive");
-  if (c.precise && c.head_dim == 256) return fail(B2_ERR_ARG, "precise (hi/lo split) mode supports head_dim 64 and 128 only");
-  CK(cudaSetDevice(device));
-  b2_engine* e = new b2_engine();
-  e->cfg = c;
-  e->device = device;
+extern "C" void b2_engine_destroy(b2_engine* e);
+// device allocations of b2_engine_create (separate so that a failure half-way can be unwound by b2_engine_destroy)
+static int engine_alloc(b2_engine* e) {
+  const b2_config& c = e->cfg;
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   e->q_cols = c.num_attention_heads * c.head_dim;
   e->kv_cols = c.num_key_value_heads * c.head_dim;
@@ -610,6 +591,37 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
   CK(cudaMalloc(&e->rope_sin, sn.size() * 4));
   CK(cudaMemcpy(e->rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+  return B2_OK;
+}
+
+extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** out) {
+  if (!cfg || !out) return fail(B2_ERR_ARG, "null argument");
+  CKR(require_gpu(device));
+  const b2_config& c = *cfg;
+  if (c.hidden_size % 128 || c.hidden_size > 128 * NORM_MAXV)
+    return fail(B2_ERR_ARG, "hidden_size %d must be a multiple of 128 and <= %d", c.hidden_size, 128 * NORM_MAXV);
+  if (c.head_dim != 64 && c.head_dim != 128 && c.head_dim != 256)
+    return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", c.head_dim);
+  if (c.num_key_value_heads <= 0 || c.num_attention_heads % c.num_key_value_heads)
+    return fail(B2_ERR_ARG, "num_attention_heads %d must be a multiple of num_key_value_heads %d",
+                c.num_attention_heads, c.num_key_value_heads);
+  // the reference raises ValueError on the same condition (llama3.2_model_numpy.py:361-365)
+  if (c.hidden_size % c.num_attention_heads)
+    return fail(B2_ERR_ARG, "hidden_size must be divisible by num_heads (got `hidden_size`: %d and `num_heads`: %d).",
+                c.hidden_size, c.num_attention_heads);
+  if (c.intermediate_size % 64) return fail(B2_ERR_ARG, "intermediate_size %d must be a multiple of 64", c.intermediate_size);
+  if (c.vocab_size % 32) return fail(B2_ERR_ARG, "vocab_size %d must be a multiple of 32", c.vocab_size);
+  if (c.max_positions <= 0) return fail(B2_ERR_ARG, "max_positions must be positive");
+  if (c.precise && c.head_dim == 256) return fail(B2_ERR_ARG, "precise (hi/lo split) mode supports head_dim 64 and 128 only");
+  CK(cudaSetDevice(device));
+  b2_engine* e = new b2_engine();
+  e->cfg = c;
+  e->device = device;
+  const int rc = engine_alloc(e);
+  if (rc != B2_OK) {                  // e.g. out of memory: free whatever was allocated
+    b2_engine_destroy(e);
+    return rc;
+  }
   *out = e;
   return B2_OK;
 }
@@ -788,17 +800,25 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   c->pf = e->cfg.precise ? 2 : 1;
   const size_t bytes = c->plane * c->pf * 2 * e->cfg.num_hidden_layers * 2;
   if (c->pf == 2 && c->plane > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "precise-mode cache plane too large"); }
-  CK(cudaMalloc(&c->kv, bytes));
-  CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
-  CK(cudaMalloc(&c->t0_dev, 4));
-  CK(cudaMemset(c->t0_dev, 0, 4));
-  if (!e->cfg.precise) {
-    c->dec_splits = decode_splits(max_batch, e->cfg.num_key_value_heads, max_tokens);
-    CK(cudaMalloc(&c->dec_part, decode_part_floats(max_batch, e->cfg.num_attention_heads, e->cfg.head_dim) * 4));
-    CK(cudaMalloc(&c->dec_cnt, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
-    CK(cudaMemset(c->dec_cnt, 0, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
+  auto alloc = [&]() -> int {
+    CK(cudaMalloc(&c->kv, bytes));
+    CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
+    CK(cudaMalloc(&c->t0_dev, 4));
+    CK(cudaMemset(c->t0_dev, 0, 4));
+    if (!e->cfg.precise) {
+      c->dec_splits = decode_splits(max_batch, e->cfg.num_key_value_heads, max_tokens);
+      CK(cudaMalloc(&c->dec_part, decode_part_floats(max_batch, e->cfg.num_attention_heads, e->cfg.head_dim) * 4));
+      CK(cudaMalloc(&c->dec_cnt, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
+      CK(cudaMemset(c->dec_cnt, 0, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
+    }
+    CK(cudaDeviceSynchronize());       // cudaMemset is asynchronous; callers may use non-blocking streams
+    return B2_OK;
+  };
+  const int rc = alloc();
+  if (rc != B2_OK) {                   // e.g. out of memory: nothing is left behind
+    b2_cache_destroy(c);
+    return rc;
   }
-  CK(cudaDeviceSynchronize());       // cudaMemset is asynchronous; callers may use non-blocking streams
   *out = c;
   return B2_OK;
 }
