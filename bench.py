@@ -308,7 +308,7 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- e2e: the C-ABI call with HOST buffers (ids H2D, forward with all logits, last-position logits D2H) ----
-    out_host = np.empty((B, V), dtype=np.float32)
+    out_host = torch.empty((B, V), dtype=torch.float32).pin_memory().numpy()   # pinned: the D2H of the result is a DMA
     ids_np = ids_host.numpy()
     for _ in range(max(1, min(a.warmup, 2))):
         model.forward_host(ids_np, logits_mode=LOGITS_ALL_LAST_TO_HOST, out=out_host)

@@ -121,6 +121,16 @@ ATT_CASES = [
     (1, 400, 2, 1, 64, 0, 1, 100, 0.0),    # sliding window
     (1, 300, 2, 1, 256, 0, 1, 64, 50.0),   # Gemma-2 HF flags: window + soft-cap
     (1, 2048, 2, 1, 64, 0, 1, 0, 0.0),
+    # co-resident kernel (head_dim 64 / 128, S > 128): ragged S, non-causal, cache offsets that are not tile-aligned,
+    # window / soft-cap combinations, GQA ratios 1 / 3 / 8, a batch that needs several waves
+    (3, 129, 3, 3, 64, 0, 1, 0, 0.0),
+    (1, 257, 8, 1, 64, 0, 0, 0, 0.0),
+    (2, 200, 6, 2, 128, 333, 1, 0, 0.0),
+    (1, 700, 4, 2, 128, 0, 1, 150, 30.0),
+    (2, 384, 4, 4, 64, 129, 1, 97, 0.0),
+    (1, 1000, 3, 1, 128, 0, 1, 0, 50.0),
+    (16, 512, 8, 8, 64, 0, 1, 0, 0.0),
+    (1, 4096, 2, 2, 128, 0, 1, 0, 0.0),
 ]
 
 
