@@ -1,18 +1,23 @@
-// Grouped-query causal attention for prefill on sm_100a tensor cores (tcgen05 + TMEM + TMA).
+// Grouped-query attention on sm_100a (tcgen05 + TMEM + TMA for prefill, mma.sync + TMA for decode).
 //
 // Replaces, per layer, the reference's materialised chain
 //   repeat_kv -> Q.K^T / sqrt(HD) -> where(tril) -> softmax -> P.V -> transpose/reshape
 // (llama3.2_model_numpy.py:470-511; gemma2_model.py:536-577) with one kernel that never writes the
 // [B,NH,S,T] score tensor.  Options the reference lacks but BASELINE.json asks for are in-kernel
 // predicates/epilogues: sliding window and tanh soft-cap (semantics of transformers' modeling_gemma2).
-//
-// CTA = one (batch, q-head, 128-row q tile); 192 threads:
-//   warps 0-3  softmax/correction/epilogue: thread = q row (= TMEM lane)
-//   warp 4     TMA producer (Q once, K/V tiles through a 2-stage ring)
-//   warp 5     tcgen05.mma issuer:  S = Q.K^T (both K-major)  ->  TMEM[0, BNKV)
-//                                   O += P.V  (P K-major from smem, V MN-major) -> TMEM[BNKV, BNKV+HD)
 // GQA: kv head = q head / n_rep, no K/V replication (replaces repeat_kv_np, :188-204).
 // Online softmax in the exp2 domain with lazy rescaling of the TMEM-resident O accumulator.
+//
+// Kernels in this file:
+//   attn_prefill_co_kernel<HD>       prefill, head_dim 64 / 128: one 128-row q tile per CTA, TWO CTAs per SM   (default)
+//   attn_prefill_kernel<HD, NP>      prefill, one CTA per SM: head_dim 256, precise (hi/lo planes) mode, S <= 128
+//       CTA = one (batch, q-head, 128-row q tile); 192 threads:
+//         warps 0-3  softmax/correction/epilogue: thread = q row (= TMEM lane)
+//         warp 4     TMA producer (Q once, K/V tiles through a 2-stage ring)
+//         warp 5     tcgen05.mma issuer:  S = Q.K^T (both K-major)  ->  TMEM[0, BNKV)
+//                                         O += P.V  (P K-major from smem, V MN-major) -> TMEM[BNKV, BNKV+HD)
+//   attn_decode_split_kernel<HD>     decode (q_len 1): split-KV, all query heads of a kv head per CTA, mma.sync   (default)
+//   attn_decode_kernel<HD>           decode, one warp per (batch, q head) on the FMA pipe: precise mode, odd head ratios
 #pragma once
 #include "common.cuh"
 
