@@ -156,7 +156,8 @@ def test_attention_prefill(B, S, NH, NKV, HD, t0, causal, window, softcap):
                                                           (2, 32, 8, 64, 576, 0, 0.0), (1, 8, 8, 64, 1023, 0, 0.0),
                                                           (3, 16, 2, 64, 700, 0, 0.0), (2, 24, 8, 128, 3000, 0, 0.0),
                                                           (2, 8, 4, 256, 1500, 0, 0.0), (2, 8, 4, 256, 1500, 600, 50.0),
-                                                          (2, 12, 4, 128, 900, 100, 30.0), (5, 32, 8, 64, 8000, 0, 0.0)])
+                                                          (2, 12, 4, 128, 900, 100, 30.0), (5, 32, 8, 64, 8000, 0, 0.0),
+                                                          (2, 16, 1, 64, 200, 0, 0.0)])   # n_rep 16 > 8: per-head kernel
 def test_attention_decode(B, NH, NKV, HD, t0, window, softcap):
     Tmax = t0 + 4
     q = bf16_randn(B, NH * HD, seed=16)
