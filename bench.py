@@ -101,12 +101,19 @@ def cpu_reference_sample(cfg, sample_tokens, steps, warmup):
     from oracle import np_oracle as O
     W = O.to_numpy_f32(O.synth_weights(cfg, seed=0, std=0.02))
     ids = np.random.default_rng(0).integers(0, cfg.vocab_size, (1, sample_tokens))
+    try:        # every host core for the BLAS calls, also when a launcher (torchrun) exported OMP_NUM_THREADS=1
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        limit = None
     for _ in range(warmup):
         O.forward(cfg, W, ids, faithful=True, keep_attn=True)
     t = time.perf_counter()
     for _ in range(steps):
         O.forward(cfg, W, ids, faithful=True, keep_attn=True)   # the reference retains attentions by default (:785-786)
     dt = (time.perf_counter() - t) / max(steps, 1)
+    if limit is not None:
+        limit.restore_original_limits()
     return sample_tokens / dt, dt
 
 
