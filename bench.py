@@ -79,22 +79,6 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def synth_weights_fast(cfg, seed, device):
-    """Random-init bf16 checkpoint of the named architecture (no network for real weights): N(0, 0.02),
-    norm gains 1.  Drawn on the GPU for speed, handed to the engine as host tensors."""
-    import torch
-    from oracle import np_oracle as O
-    g = torch.Generator(device=device).manual_seed(seed)
-    out = {}
-    for n in O.weight_names(cfg):
-        shp = O.weight_shape(cfg, n)
-        if len(shp) == 1:
-            out[n] = torch.full(shp, 0.0 if cfg.family == "gemma2" else 1.0, dtype=torch.bfloat16)
-        else:
-            out[n] = (torch.randn(shp, generator=g, device=device, dtype=torch.float32) * 0.02).to(torch.bfloat16).cpu()
-    return out
-
-
 def cpu_reference_sample(cfg, sample_tokens, steps, warmup):
     """Times the reference's CPU path (oracle port issuing the reference's own NumPy calls, faithful=True)
     on a bounded sample: one sequence of `sample_tokens` tokens per step."""
@@ -221,8 +205,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
 
-    from oracle import np_oracle as O
-    cfg = O.gemma2_config("2b") if a.model == "gemma2-2b" else O.llama_config(a.model)
+    from llm_np_cp_b200 import shapes          # presets / FLOP arithmetic live in the product package; oracle/ is only
+    cfg = shapes.gemma2_config("2b") if a.model == "gemma2-2b" else shapes.llama_config(a.model)   # imported by the CPU legs
     if a.batch <= 0:
         a.batch = 8 if a.workload == "prefill" else 64
     rank = int(os.environ.get("RANK", 0))
@@ -232,7 +216,7 @@ def main():
     workload = (f"{fam} prefill seq={a.seq}" + (" hf-flags" if a.hf_flags else "") if a.workload == "prefill" else
                 f"{fam} decode batch={a.batch} prompt={a.prompt} new={a.new_tokens}")
     pk = peaks()
-    f_tok = O.flops_per_token(cfg, a.seq)
+    f_tok = shapes.flops_per_token(cfg, a.seq)
 
     if a.impl == "reference":
         # the reference's own CPU implementation of the path, on this box's host cores; rank 0 only
@@ -264,7 +248,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B, S, V = a.batch, a.seq, cfg.vocab_size
-    w = synth_weights_fast(cfg, seed=0, device=dev)
+    w = shapes.synth_checkpoint(cfg, seed=0, device=dev)
     if cfg.family == "gemma2":
         model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16), hf_flags=a.hf_flags)
     else:

@@ -53,3 +53,19 @@ def test_interleave_gate_up_host_helper():
     rc = _lib.lib().b2_interleave_gate_up(g.ctypes.data, u.ctypes.data, out.ctypes.data, I, H)
     assert rc == 0
     assert (out[:32] == g[:32]).all() and (out[32:64] == u[:32]).all() and (out[64:96] == g[32:]).all()
+
+
+def test_shape_presets_match_the_oracle_copy():
+    """llm_np_cp_b200.shapes (what bench.py's GPU arm uses) restates the same public configs, tensor names / shapes and
+    FLOP arithmetic as the oracle's independent copy."""
+    from llm_np_cp_b200 import shapes
+    from oracle import np_oracle as O
+    for mine, ref in [(shapes.llama_config("1b"), O.llama_config("1b")), (shapes.llama_config("3b"), O.llama_config("3b")),
+                      (shapes.llama_config("tiny"), O.llama_config("tiny")), (shapes.gemma2_config("2b"), O.gemma2_config("2b")),
+                      (shapes.gemma2_config("tiny"), O.gemma2_config("tiny"))]:
+        for k, v in ref.items():
+            assert mine[k] == v, k
+        assert shapes.weight_names(mine) == O.weight_names(ref)
+        assert all(shapes.weight_shape(mine, n) == O.weight_shape(ref, n) for n in O.weight_names(ref))
+        for S in (16, 2048, 8192):
+            assert shapes.flops_per_token(mine, S) == O.flops_per_token(ref, S)
