@@ -80,36 +80,54 @@ class ClockSampler:
 
 
 def cpu_reference_sample(cfg, sample_tokens, steps, warmup):
-    """Times the reference's CPU path (oracle port issuing the reference's own NumPy calls, faithful=True)
-    on a bounded sample: one sequence of `sample_tokens` tokens per step."""
+    """Times the reference's CPU path on a bounded sample (one sequence of `sample_tokens` tokens per step, default
+    arguments of model(ids): attentions and hidden states retained, llama3.2_model_numpy.py:785-786).
+    kind "reference": the reference's OWN LlamaForCausalLM_np, loaded from /root/reference when mounted or from the
+    byte-compiled build oracle/_ref (oracle/build_ref.py) on the GPU box, weights injected through its `weights` seam.
+    kind "port": the oracle port issuing the reference's own N-D np.dot calls (faithful=True) when neither exists (or the
+    model is Gemma-2, whose reference file is CuPy-only)."""
     from oracle import np_oracle as O
-    W = O.to_numpy_f32(O.synth_weights(cfg, seed=0, std=0.02))
+    from oracle import ref_harness as R
+    w = O.synth_weights(cfg, seed=0, std=0.02)
     ids = np.random.default_rng(0).integers(0, cfg.vocab_size, (1, sample_tokens))
     try:        # every host core for the BLAS calls, also when a launcher (torchrun) exported OMP_NUM_THREADS=1
         from threadpoolctl import threadpool_limits
         limit = threadpool_limits(limits=os.cpu_count() or 1)
     except Exception:
         limit = None
+    kind = "port"
+    if cfg.family == "llama" and R.available():
+        try:
+            mod = R.load_llama_numpy()
+            model, _ = R.build_reference_model(mod, cfg, w)
+            step = lambda: model(ids, use_cache=False)           # noqa: E731  the reference's own __call__
+            kind = "reference"
+        except Exception as e:                                    # a broken build of oracle/_ref must not kill the bench
+            sys.stderr.write(f"[bench] reference module unavailable ({e!r}); timing the NumPy port instead\n")
+    if kind == "port":
+        W = O.to_numpy_f32(w)
+        step = lambda: O.forward(cfg, W, ids, faithful=True, keep_attn=True)   # noqa: E731
     for _ in range(warmup):
-        O.forward(cfg, W, ids, faithful=True, keep_attn=True)
+        step()
     t = time.perf_counter()
     for _ in range(steps):
-        O.forward(cfg, W, ids, faithful=True, keep_attn=True)   # the reference retains attentions by default (:785-786)
+        step()
     dt = (time.perf_counter() - t) / max(steps, 1)
     if limit is not None:
         limit.restore_original_limits()
-    return sample_tokens / dt, dt
+    return sample_tokens / dt, dt, kind
 
 
-def bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload):
-    """BASELINE.json config #5: autoregressive decode with the KV cache, B sequences per GPU (replicas only across
-    GPUs), greedy feedback on the device, whole step replayed as a CUDA graph.  A "step" = one rollout of
-    `new_tokens` one-token forwards for the batch; the prompt prefill is outside the timed region."""
+def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, steps, warmup, sample_clocks=True):
+    """BASELINE.json config #5: autoregressive decode with the KV cache (the loop of generate(),
+    llama3.2_model_numpy.py:881-909): B sequences per GPU (replicas only across GPUs), greedy feedback on the device, every
+    one-token step replayed as one CUDA graph.  One rollout = `NT` one-token forwards for the batch; the prompt prefill is
+    outside the timed region.  Returns the dict that goes into the JSON line (rank 0) or None."""
     import torch
     import llm_np_cp_b200 as M
     from llm_np_cp_b200.model import LOGITS_LAST
     from llm_np_cp_b200 import dp
-    B, P, NT, V = a.batch, a.prompt, a.new_tokens, cfg.vocab_size
+    V = cfg.vocab_size
     rng = np.random.default_rng(99 + rank)
     prompt = torch.from_numpy(rng.integers(0, V, (B, P)).astype(np.int64)).to(dev)
     cache = M.KVCache(max_batch=B, max_tokens=P + NT)
@@ -142,50 +160,70 @@ def bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         rollout(False)
     barrier()
     model.reset_stats()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if sample_clocks else None
+    if rank == 0 and sampler:
         sampler.start()
     ms = 0.0
-    for _ in range(a.steps):
+    for _ in range(steps):
         ms += rollout(False)[0]
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and sampler) else None
     launches = model.stats()["launches"]
     e2e_ms = 0.0
-    for _ in range(a.steps):
+    for _ in range(steps):
         e2e_ms += rollout(True)[1]
+    model.set_decode_graph(False)
     ms, e2e_ms = dp.max_over_ranks([ms, e2e_ms], device=dev)
-    toks = B * NT * world * a.steps
+    toks = B * NT * world * steps
+    if rank != 0:
+        return None
+    from llm_np_cp_b200 import shapes
+    L = cfg.num_hidden_layers
+    kv = cfg.num_key_value_heads * cfg.head_dim
+    t_avg = P + NT / 2.0
+    bytes_step = 2.0 * shapes.matmul_params(cfg) + B * t_avg * L * 2 * kv * 2   # bf16 weights once + KV read
+    step_s = ms / 1e3 / (steps * NT)
+    gbs = bytes_step / step_s / 1e9
+    return {
+        "metric": "decode_tokens_per_sec", "value": toks / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "config": {"batch_per_gpu": B, "prompt": P, "new_tokens": NT,
+                   "parallelism": f"replicas x{world} (no collective)", "sampling": "greedy argmax on device (b2_argmax)",
+                   "cuda_graph": not os.environ.get("B2_NO_GRAPH"),
+                   "l2": "all weights (2.47 GB for 1B) streamed every token step >> 126 MB L2; no flush needed"},
+        "ms_per_token_step": step_s * 1e3,
+        "roofline": {"bound": "hbm", "kernel": "whole token step (weight-streaming GEMMs at M = batch + split-KV attention)",
+                     "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                     "bytes_per_token_step": bytes_step, "peak_source": pk["src"] + " hbm_gbs"},
+        "e2e": {"value": toks / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": B * 8 * NT * world,
+                "d2h_bytes_per_step": B * 8 * NT * world,
+                "what": "per token: sampled ids D2H, ids H2D, one-token forward through model(), greedy pick"},
+        "gpu_launches": int(launches), "clocks": clocks}
+
+
+def bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload):
+    """`--workload decode`: the decode rollout as the headline line."""
+    line = measure_decode(cfg, model, dev, dist, rank, world, local, pk, a.batch, a.prompt, a.new_tokens, a.steps, a.warmup)
     if rank == 0:
-        L, H, I = cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size
-        q, kv = cfg.num_attention_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim
-        p_mm = L * (H * q + 2 * H * kv + q * H + 3 * H * I) + V * H
-        t_avg = P + NT / 2.0
-        bytes_step = 2.0 * p_mm + B * t_avg * L * 2 * kv * 2            # bf16 weights once + KV read
-        step_s = ms / 1e3 / (a.steps * NT)
-        gbs = bytes_step / step_s / 1e9
-        print(json.dumps({
-            "metric": "decode_tokens_per_sec", "value": toks / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "batch_per_gpu": B, "prompt": P, "new_tokens": NT,
-                       "parallelism": f"replicas x{world} (no collective)", "sampling": "greedy argmax on device (b2_argmax)",
-                       "cuda_graph": True, "l2": "2.47 GB of weights streamed per token step >> 126 MB L2"},
-            "ms_per_token_step": step_s * 1e3,
-            "roofline": {"bound": "hbm", "kernel": "gemm_bf16_kernel (weight streaming, M=batch)", "achieved": gbs,
-                         "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
-                         "bytes_per_token_step": bytes_step, "peak_source": pk["src"] + " hbm_gbs"},
-            "e2e": {"value": toks / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": B * 8 * NT * world,
-                    "d2h_bytes_per_step": B * 8 * NT * world,
-                    "what": "per token: sampled ids D2H, ids H2D, one-token forward through model(), greedy pick"},
-            "gpu_launches": int(launches), "clocks": clocks}))
+        line["config"] = dict({"workload": workload}, **line["config"])
+        line.update({"vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
+        print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def prefill_config(cfg, fam, workload, B, S, world):
+    """The `config` object of the prefill line: identical in the engine's arm and in `--impl reference`."""
+    return {"workload": workload, "model": f"{fam} shapes, random-init bf16 weights (std 0.02)",
+            "global_batch": B * world, "seq_len": S, "tokens_per_step_per_gpu": B * S,
+            "parallelism": f"dp{world} (batch-sharded, weights replicated, no collective)",
+            "logits": "full [B,S,V] fp32 written to HBM every step",
+            "l2": "per-step working set (2.5 GB weights + 8.4 GB logits + activations) >> 126 MB L2; no flush needed"}
 
 
 def main():
@@ -202,7 +240,12 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (default 8 prefill / 64 decode)")
     ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--cpu-sample-tokens", type=int, default=int(os.environ.get("B2_CPU_SAMPLE_TOKENS", 16)))
+    ap.add_argument("--cpu-long-sample", type=int, default=int(os.environ.get("B2_CPU_LONG_SAMPLE", 128)),
+                    help="--impl reference: one extra forward at this many tokens (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="prefill workload: skip the appended config-#5 decode rollout")
+    ap.add_argument("--no-precise", action="store_true", help="prefill workload: skip the parity-mode (hi/lo split) measurement")
+    ap.add_argument("--event-every", type=int, default=4, help="per-launch CUDA events on every k-th timed step only")
     a = ap.parse_args()
 
     from llm_np_cp_b200 import shapes          # presets / FLOP arithmetic live in the product package; oracle/ is only
@@ -219,20 +262,31 @@ def main():
     f_tok = shapes.flops_per_token(cfg, a.seq)
 
     if a.impl == "reference":
-        # the reference's own CPU implementation of the path, on this box's host cores; rank 0 only
+        # the reference's own CPU implementation of the path, on this box's host cores; rank 0 only.  Each step is a
+        # bounded sample of the workload: ONE sequence of --cpu-sample-tokens tokens (default 16 = BASELINE config #1,
+        # ~10 s on 128 cores) so that --steps 20 --warmup 5 ends within a few minutes; one extra forward at a longer sample
+        # (--cpu-long-sample, default 128 tokens) is reported beside it.
         if rank != 0:
             return
-        tps, dt = cpu_reference_sample(cfg, a.cpu_sample_tokens, a.steps, a.warmup)
+        tps, dt, kind = cpu_reference_sample(cfg, a.cpu_sample_tokens, a.steps, a.warmup)
         cores = os.cpu_count()
-        sample = f"1 sequence x {a.cpu_sample_tokens} tokens per step (NumPy {np.__version__}, {cores} BLAS threads)"
-        print(json.dumps({
+        sample = (f"1 sequence x {a.cpu_sample_tokens} tokens per step through "
+                  f"{'the reference module (LlamaForCausalLM_np, oracle/_ref build)' if kind == 'reference' else 'the NumPy port (reference N-D np.dot calls)'}"
+                  f", NumPy {np.__version__}, {cores} BLAS threads")
+        line = {
             "impl": "reference", "metric": "prefill_tokens_per_sec", "value": tps, "unit": "tokens/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32/f64 (NumPy)", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": prefill_config(cfg, fam, workload, a.batch, a.seq, a.gpus),
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample,
+                             "sample_tokens": a.cpu_sample_tokens},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0}
+        if a.cpu_long_sample > a.cpu_sample_tokens:
+            tps2, dt2, kind2 = cpu_reference_sample(cfg, a.cpu_long_sample, 1, 0)
+            line["cpu_baseline_long"] = {"value": tps2, "unit": "tokens/s", "cores": cores, "kind": kind2, "seconds": dt2,
+                                         "sample": f"1 sequence x {a.cpu_long_sample} tokens, 1 forward", "sample_tokens": a.cpu_long_sample}
+        print(json.dumps(line))
         return
 
     import torch
@@ -253,8 +307,8 @@ def main():
         model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16), hf_flags=a.hf_flags)
     else:
         model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16))
-    del w
     if a.workload == "decode":
+        del w
         return bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload)
     rng = np.random.default_rng(1234 + rank)
     ids_host = torch.from_numpy(rng.integers(0, V, (B, S)).astype(np.int64)).pin_memory()
@@ -273,16 +327,19 @@ def main():
                                    logits_mode=LOGITS_ALL)
 
     # ---- value: inputs resident in HBM ----
+    # Per-launch CUDA events (the roofline figures) are recorded on every --event-every-th step only: events between
+    # launches defeat the programmatic-dependent-launch overlap, so most timed steps run exactly what e2e runs.
     for _ in range(a.warmup):
         step_resident()
     logits = None
     barrier()
     model.reset_stats()
-    model.set_timing(True)
+    model.set_timing(max(1, a.event_every))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         step_resident()        # one extra untimed step so nvidia-smi is sampling under load before t0
+    model.set_timing(max(1, a.event_every))   # restart the every-k-th counter; first timed step carries events
     model.reset_stats()        # only the timed steps below count towards the roofline figures
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -295,6 +352,7 @@ def main():
     ms = e0.elapsed_time(e1)
     st = model.stats()
     model.set_timing(False)
+    fast_last = logits[:, -1, :].clone() if (world == 1 and not a.no_precise) else None
     logits = None
     torch.cuda.empty_cache()
 
@@ -318,35 +376,73 @@ def main():
     value = tokens / (ms / 1e3)
     e2e = tokens / (e2e_ms / 1e3)
 
+    # ---- decode: BASELINE's metric ends "...; decode tok/s" -- a short config-#5 rollout rides along in the same line ----
+    decode = None
+    if not a.no_decode and cfg.family == "llama":
+        decode = measure_decode(cfg, model, dev, dist, rank, world, local, pk, 64, 16, 128, steps=3, warmup=1, sample_clocks=False)
+
+    # ---- parity mode: what BASELINE's literal "1e-2 max-abs" costs.  Same kernels, every bf16 activation carried as hi + lo
+    # ---- planes (logits within ~2e-4 of the reference, tests/test_gpu_model.py).  Labelled, never the headline.
+    precise = None
+    if fast_last is not None and cfg.head_dim in (64, 128, 256):
+        try:
+            cls = M.Gemma2ForCausalLM if cfg.family == "gemma2" else M.LlamaForCausalLM
+            kw = dict(hf_flags=a.hf_flags) if cfg.family == "gemma2" else {}
+            pm = cls(M.AttributeDict(cfg), w, device=local, max_positions=max(S, 16), precise=True, **kw)
+            for _ in range(2):
+                _, plog, _, _, _ = pm(ids_dev, use_cache=False, output_hidden_states=False, logits_mode=LOGITS_ALL)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            psteps = 3
+            p0.record()
+            for _ in range(psteps):
+                _, plog, _, _, _ = pm(ids_dev, use_cache=False, output_hidden_states=False, logits_mode=LOGITS_ALL)
+            p1.record()
+            torch.cuda.synchronize()
+            pms = p0.elapsed_time(p1) / psteps
+            diff = (plog[:, -1, :] - fast_last).abs()
+            precise = {"parity_mode": "hi/lo split-bf16 activations (b2_config.precise): logits within 1e-2 max-abs of the reference",
+                       "value": B * S / (pms / 1e3), "unit": "tokens/s", "ms_per_step": pms, "steps": psteps,
+                       "slowdown_vs_fast": pms / (ms / a.steps),
+                       "fast_vs_precise_last_logits": {"max_abs": float(diff.max()), "mean_abs": float(diff.mean()),
+                                                       "logit_std": float(plog[:, -1, :].std())},
+                       "note": "not the headline: never quote throughput from this mode without the label"}
+            del pm, plog
+        except Exception as ex:      # e.g. a head_dim the precise attention does not cover
+            precise = {"parity_mode": "unavailable", "why": str(ex)[:200]}
+        torch.cuda.empty_cache()
+    del w
+
     if rank == 0:
+        nt = max(1, int(st["timed_forwards"]))      # steps whose launches carried events
         gemm_tf = st["gemm_flops"] / (st["gemm_ms"] * 1e-3) / 1e12 if st["gemm_ms"] > 0 else None
         attn_tf = st["attn_flops"] / (st["attn_ms"] * 1e-3) / 1e12 if st["attn_ms"] > 0 else None
         peak = pk["tf_sustained"]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-        if a.model == "1b" and S == 2048 and B == 8 and os.path.exists(tpath):   # the ncu capture is for exactly this workload
-            with open(tpath) as f:
-                traffic = json.load(f)["avg_dram_bytes_per_gemm_launch"]
+        traffic, tsrc = None, None
+        for tname in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if a.model == "1b" and S == 2048 and B == 8 and os.path.exists(tpath):   # the ncu capture is for exactly this workload
+                with open(tpath) as f:
+                    traffic, tsrc = json.load(f)["avg_dram_bytes_per_gemm_launch"], tname
+                break
+        step_ms = ms / a.steps
         line = {
             "metric": "prefill_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "model": f"{fam} shapes, random-init bf16 weights (std 0.02)",
-                       "global_batch": B * world, "seq_len": S, "tokens_per_step_per_gpu": B * S,
-                       "parallelism": f"dp{world} (batch-sharded, weights replicated, no collective)",
-                       "logits": "full [B,S,V] fp32 written to HBM every step",
-                       "l2": "per-step working set (2.5 GB weights + 8.4 GB logits + activations) >> 126 MB L2; no flush needed"},
+            "config": prefill_config(cfg, fam, workload, B, S, world),
             "model_flops_per_token": f_tok,
             "model_tflops_per_gpu": value / world * f_tok / 1e12,
             "model_frac_of_peak": value / world * f_tok / 1e12 / peak,
             "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, all fused-epilogue variants)",
                          "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": traffic,
-                         "traffic_note": "avg DRAM bytes per GEMM launch from profiles/r01_gemm_traffic.json (ncu --set full); algorithmic 507 MB",
+                         "traffic_note": f"avg DRAM bytes per GEMM launch from profiles/{tsrc} (ncu --set full); algorithmic 507 MB",
                          "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                         "gemm_ms_per_step": st["gemm_ms"] / a.steps, "gemm_share_of_step": st["gemm_ms"] / ms,
-                         "attention": {"achieved": attn_tf, "ms_per_step": st["attn_ms"] / a.steps,
-                                       "share_of_step": st["attn_ms"] / ms}},
+                         "events_on_steps": f"{nt} of {a.steps} timed steps (every {max(1, a.event_every)}th)",
+                         "gemm_ms_per_step": st["gemm_ms"] / nt, "gemm_share_of_step": st["gemm_ms"] / nt / step_ms,
+                         "attention": {"achieved": attn_tf, "ms_per_step": st["attn_ms"] / nt,
+                                       "share_of_step": st["attn_ms"] / nt / step_ms}},
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8 * world, "d2h_bytes_per_step": B * V * 4 * world,
                     "ms_per_step": e2e_ms / a.steps,
                     "what": "b2_forward_host: ids from host, all-position logits kept on device (like the reference's CuPy twin), "
@@ -354,11 +450,17 @@ def main():
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
         }
+        if decode is not None:
+            line["decode"] = decode
+        if precise is not None:
+            line["precise"] = precise
         if world == 1 and not a.no_cpu_baseline:
-            tps, dt = cpu_reference_sample(cfg, a.cpu_sample_tokens, 1, 0)
-            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"1 sequence x {a.cpu_sample_tokens} tokens, 1 timed forward of the NumPy port issuing the "
-                                              f"reference's own N-D np.dot calls (NumPy {np.__version__})", "seconds": dt}
+            tps, dt, kind = cpu_reference_sample(cfg, a.cpu_sample_tokens, 1, 0)
+            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": kind,
+                                    "sample": f"1 sequence x {a.cpu_sample_tokens} tokens, 1 timed forward of "
+                                              + ("the reference module itself (LlamaForCausalLM_np from the oracle/_ref build)" if kind == "reference"
+                                                 else "the NumPy port issuing the reference's own N-D np.dot calls")
+                                              + f" (NumPy {np.__version__})", "seconds": dt}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

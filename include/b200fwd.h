@@ -104,6 +104,24 @@ int b2_cache_read(const b2_cache* c, int layer, int which /*0=K,1=V*/, int batch
  * stream      cudaStream_t; NULL is the CUDA default stream, as everywhere in CUDA              */
 int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids_dev, int B, int S, int logits_mode,
                float* logits_dev, float* hidden_dev, void* stream);
+/* Extended form of b2_forward: everything LlamaModel.__call__ accepts on the path (llama3.2_model_numpy.py:624-732).
+ * Exactly one of ids / inputs_embeds must be non-NULL (the reference raises ValueError otherwise, :645-652). */
+typedef struct b2_forward_args {
+  const int64_t* ids;           /* device int64 [B,S], or NULL */
+  const float* inputs_embeds;   /* device fp32 [B,S,H] used instead of the embedding gather (:675-676), or NULL */
+  const int32_t* position_ids;  /* device int32 [S]: RoPE positions (:657), shared by the batch like the reference's [1,S];
+                                   NULL = cache length + s.  K/V are always appended at cache length + s. */
+  int32_t B, S, logits_mode;
+  float* logits;                /* device, per logits_mode */
+  float* hidden;                /* optional device fp32 [L+1,B,S,H] */
+  float* attn_probs;            /* optional device fp32 [L,B,NH,S,T], T = cached + S: opt-in debug materialisation of the
+                                   reference's `attentions` tuple (:713-714); recomputed per layer by a separate kernel */
+  void* stream;
+} b2_forward_args;
+int b2_forward_ex(b2_engine* e, b2_cache* cache, const b2_forward_args* args);
+/* HF layer_types: is_sliding[i] != 0 => layer i applies cfg.sliding_window (default without this call: even layers,
+ * transformers' Gemma-2 default pattern).  No effect while cfg.sliding_window == 0 (the reference never slides). */
+int b2_set_layer_types(b2_engine* e, const int32_t* is_sliding, int n_layers);
 /* Same call with HOST buffers (pageable or pinned): ids H2D, forward, logits D2H, synchronises. */
 int b2_forward_host(b2_engine* e, b2_cache* cache, const int64_t* ids_host, int B, int S, int logits_mode,
                     float* logits_host, float* hidden_host);
@@ -129,8 +147,11 @@ typedef struct b2_stats {
   double attn_ms;
   double attn_flops;
   int64_t attn_launches;
+  int64_t timed_forwards;  /* forwards whose launches carried events (see b2_set_timing) */
 } b2_stats;
-int b2_set_timing(b2_engine* e, int on);          /* record CUDA events around GEMM / attention launches */
+/* on = 1: record CUDA events around every GEMM / attention launch; on = k > 1: only on every k-th forward (the other
+ * forwards take the plain launch path, so a timed region mostly runs exactly what an untimed one runs); 0 = off */
+int b2_set_timing(b2_engine* e, int on);
 int b2_get_stats(b2_engine* e, b2_stats* out);    /* synchronises the engine stream when timing is on */
 int b2_reset_stats(b2_engine* e);
 

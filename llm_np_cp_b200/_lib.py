@@ -25,7 +25,13 @@ class B2Config(C.Structure):
 class B2Stats(C.Structure):
     _fields_ = [("launches", C.c_int64), ("gemm_launches", C.c_int64), ("gemm_ms", C.c_double),
                 ("gemm_flops", C.c_double), ("attn_ms", C.c_double), ("attn_flops", C.c_double),
-                ("attn_launches", C.c_int64)]
+                ("attn_launches", C.c_int64), ("timed_forwards", C.c_int64)]
+
+
+class B2ForwardArgs(C.Structure):
+    _fields_ = [("ids", C.c_void_p), ("inputs_embeds", C.c_void_p), ("position_ids", C.c_void_p),
+                ("B", C.c_int32), ("S", C.c_int32), ("logits_mode", C.c_int32),
+                ("logits", C.c_void_p), ("hidden", C.c_void_p), ("attn_probs", C.c_void_p), ("stream", C.c_void_p)]
 
 
 # every symbol include/b200fwd.h declares: (name, restype, argtypes)
@@ -43,6 +49,8 @@ SYMBOLS = [
     ("b2_cache_reset", _I, [_P]),
     ("b2_cache_read", _I, [_P, _I, _I, _I, _P]),
     ("b2_forward", _I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    ("b2_forward_ex", _I, [_P, _P, C.POINTER(B2ForwardArgs)]),
+    ("b2_set_layer_types", _I, [_P, C.POINTER(C.c_int32), _I]),
     ("b2_forward_host", _I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     ("b2_set_decode_graph", _I, [_P, _I]),
     ("b2_sample_min_p", _I, [_P, _P, _I, _I, _F, _P, _P, _P, _P]),

@@ -24,16 +24,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    # B2_DEFINES="-DB2_DIAG -DATT_POLY=1" etc.: bring-up / A-B builds (tools/gpu_diag.py tracing needs -DB2_DIAG)
+    defines = os.environ.get("B2_DEFINES", "").split()
+    out = os.environ.get("B2_LIB_OUT", LIB)
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
-           "-Xptxas", "-v" if verbose else "-warn-spills",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xptxas", "-v" if verbose else "-warn-spills"] + defines + [
+           "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libb200fwd.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

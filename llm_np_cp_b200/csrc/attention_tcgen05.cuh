@@ -61,6 +61,9 @@ struct AttTrace {
 #ifndef ATT_POLY
 #define ATT_POLY 0
 #endif
+#ifndef ATT_POLY_MOD
+#define ATT_POLY_MOD 4
+#endif
 constexpr int ATT_BM = 128;
 constexpr int ATT_THREADS = 192;
 
@@ -116,9 +119,9 @@ __device__ __forceinline__ void att_exp32(const uint32_t (&sr)[32], int c, uint8
     if (CAP) x = fmaf(fast_tanh(sv * cap_in), cap_out, -m_safe);   // cap*log2e*tanh(s*scale/cap) - m
     else x = fmaf(sv, sl2, -m_safe);
     if (MASK) x = static_cast<unsigned>(rel + i) < span ? x : -INFINITY;
-    // MUFU.EX2 is the bottleneck of this loop (quarter-rate pipe): ATT_POLY of every 4 exponentials run on the
+    // MUFU.EX2 is the bottleneck of this loop (quarter-rate pipe): ATT_POLY of every ATT_POLY_MOD exponentials run on the
     // FMA pipe instead (compile-time pattern, so both paths are straight-line code)
-    e[i] = ((i & 3) < ATT_POLY) ? poly_exp2(x) : fast_exp2(x);
+    e[i] = ((i % ATT_POLY_MOD) < ATT_POLY) ? poly_exp2(x) : fast_exp2(x);
   }
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {

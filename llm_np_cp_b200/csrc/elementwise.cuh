@@ -30,6 +30,76 @@ embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict_
   }
 }
 
+// x = inputs_embeds * scale (caller-provided embeddings instead of token ids, llama3.2_model_numpy.py:645-676;
+// Gemma-2 multiplies by sqrt(H) afterwards, gemma2_model.py:738-739).  n4 = number of float4.
+__global__ void __launch_bounds__(256)
+scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n4, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = s4[i];
+    d4[i] = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+  }
+}
+
+// Opt-in debug path: materialises one layer's attention probabilities [B,NH,S,T] fp32 -- the `attentions` tuple the
+// reference returns by default (llama3.2_model_numpy.py:501, :713-714) and the fused attention kernels never form.
+// Recomputed from this layer's post-RoPE q and its K cache (hi planes): one warp per (batch, head, query) row, three
+// passes over the row (scores, exp, normalise).  Not on the product path; parity tests compare it with the goldens.
+__global__ void __launch_bounds__(256)
+attn_probs_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kc, float* __restrict__ out,
+                  int B, int S, int NH, int NKV, int HD, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap,
+                  int causal, int window) {
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t row = static_cast<size_t>(blockIdx.x) * 8 + warp;
+  if (row >= static_cast<size_t>(B) * NH * S) return;
+  const int s = static_cast<int>(row % S), h = static_cast<int>((row / S) % NH), b = static_cast<int>(row / (static_cast<size_t>(S) * NH));
+  const int t0 = *t0_ptr, T = t0 + S, qpos = t0 + s;
+  const int lo = window > 0 ? max(0, qpos - window + 1) : 0;
+  const int hi = causal ? qpos : T - 1;
+  const uint4* q4 = reinterpret_cast<const uint4*>(q + (static_cast<size_t>(b) * S + s) * ldq + h * HD);
+  const __nv_bfloat16* kb = kc + static_cast<size_t>(b * NKV + h / (NH / NKV)) * Tmax * HD;
+  float* o = out + row * T;
+  float m = -INFINITY;
+  for (int t = lane; t < T; t += 32) {
+    float v = -INFINITY;
+    if (t >= lo && t <= hi) {
+      const uint4* k4 = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(t) * HD);
+      float acc = 0.f;
+      for (int i = 0; i < HD / 8; ++i) {
+        const uint4 a = __ldg(q4 + i), c = __ldg(k4 + i);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = __bfloat1622float2(a2[e]), y = __bfloat1622float2(c2[e]);
+          acc = fmaf(x.x, y.x, acc);
+          acc = fmaf(x.y, y.y, acc);
+        }
+      }
+      v = acc * scale;
+      if (softcap > 0.f) v = softcap * tanhf(v / softcap);
+    }
+    o[t] = v;
+    m = fmaxf(m, v);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int t = lane; t < T; t += 32) {
+    const float v = o[t];
+    const float e = (v == -INFINITY) ? 0.f : expf(v - m);
+    o[t] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  for (int t = lane; t < T; t += 32) o[t] *= inv;
+}
+
 constexpr int NORM_MAXV = 24;  // float4 per lane: supports H <= 3072
 
 // out = x * 1/sqrt(mean(x^2)+eps) * g   (LlamaRMSNorm_np, llama3.2_model_numpy.py:256-278; g already holds

@@ -1,11 +1,13 @@
 // libb200fwd.so -- C ABI (include/b200fwd.h) over the hand-written sm_100a kernels.
 // Host side only orchestrates: device memory, TMA descriptors, launch order, CUDA graph for decode.
 // There is no CPU compute path: without an sm_100 device every compute call fails with B2_ERR_NO_GPU.
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <map>
 #include <string>
 #include <tuple>
@@ -60,8 +62,10 @@ extern "C" int b2_device_count(void) {
 }
 
 static int require_gpu(int device) {
-  static bool ok[64] = {};                     // a device that passed once is not re-queried (cudaGetDeviceProperties is ~1 ms)
-  if (device >= 0 && device < 64 && ok[device]) return B2_OK;
+  // a device that passed once is not re-queried (cudaGetDeviceProperties is ~1 ms); atomic: engines on different
+  // devices may be created from different host threads
+  static std::atomic<uint64_t> ok{0};
+  if (device >= 0 && device < 64 && ((ok.load(std::memory_order_acquire) >> device) & 1ull)) return B2_OK;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
     cudaGetLastError();
@@ -72,7 +76,7 @@ static int require_gpu(int device) {
   CK(cudaGetDeviceProperties(&p, device));
   if (p.major != 10)
     return fail(B2_ERR_NO_GPU, "device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
-  if (device < 64) ok[device] = true;
+  if (device < 64) ok.fetch_or(1ull << device, std::memory_order_release);
   return B2_OK;
 }
 
@@ -122,7 +126,10 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 // ------------------------------------------------------------------------------------------
 struct Stats {
   int64_t launches = 0, gemm_launches = 0, attn_launches = 0;
-  bool timing = false;
+  bool timing = false;     // b2_set_timing(on > 0)
+  int every = 1;           // events are recorded on every `every`-th forward only
+  bool sample = false;     // this forward records events
+  int64_t forwards = 0, timed_forwards = 0;
   struct Ev {
     cudaEvent_t a, b;
     double flops;
@@ -154,28 +161,40 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-static int g_num_sms[16] = {0};
+// SM count of the current device (queried once per device; atomics: one host thread per engine is allowed)
+static std::atomic<int> g_num_sms[64];
 static int num_sms() {
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 16 && g_num_sms[dev]) return g_num_sms[dev];
+  if (dev >= 0 && dev < 64) {
+    const int c = g_num_sms[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
   int n = 148;
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  if (dev < 16) g_num_sms[dev] = n;
+  if (dev >= 0 && dev < 64) g_num_sms[dev].store(n, std::memory_order_relaxed);
   return n;
+}
+
+// cudaFuncSetAttribute(max dynamic smem) once per (kernel instantiation, device).  `mask` is the instantiation's own
+// static bit set; a benign double-set under a race is harmless, the atomic keeps it data-race free.
+template <typename Kern>
+static int smem_attr_once(Kern kern, int bytes, std::atomic<uint64_t>& mask, bool max_carveout = false) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull)) return B2_OK;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (max_carveout) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+  return B2_OK;
 }
 
 template <int BN, int EPI>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                          cudaStream_t st) {
   auto kern = gemm_bf16_kernel<BN, EPI>;
-  static bool attr[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 16 || !attr[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
-    if (dev < 16) attr[dev] = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  CKR(smem_attr_once(kern, GemmCfg<BN>::SMEM_BYTES, attr));
   const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM, n_blocks = (p.N + BN - 1) / BN;
   const int total = m_blocks * n_blocks * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
@@ -188,13 +207,8 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 template <int EPI>
 static int launch_gemm2_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmParams p, cudaStream_t st) {
   auto kern = gemm2_bf16_kernel<EPI>;
-  static bool attr[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 16 || !attr[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
-    if (dev < 16) attr[dev] = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  CKR(smem_attr_once(kern, Gemm2Cfg::SMEM_BYTES, attr));
   p.band_m = p.band_m > 1 ? p.band_m / 2 : 1;          // bands are counted in 256-row tiles here
   const int total = ((p.M + 255) / 256) * ((p.N + 255) / 256);
   int clusters = num_sms() / 2;
@@ -249,13 +263,8 @@ template <int HD, int NP>
 static int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                          cudaStream_t st) {
   auto kern = attn_prefill_kernel<HD, NP>;
-  static bool attr[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 16 || !attr[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<HD, NP>::SMEM_BYTES));
-    if (dev < 16) attr[dev] = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  CKR(smem_attr_once(kern, AttnCfg<HD, NP>::SMEM_BYTES, attr));
   dim3 grid((p.S + ATT_BM - 1) / ATT_BM, p.NH, p.B);
   CK(launch_k(kern, grid, dim3(ATT_THREADS), AttnCfg<HD, NP>::SMEM_BYTES, st, tq, tk, tv, p));
   return B2_OK;
@@ -265,14 +274,8 @@ template <int HD>
 static int launch_attn_co_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                             cudaStream_t st) {
   auto kern = attn_prefill_co_kernel<HD>;
-  static bool attr[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 16 || !attr[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCoCfg<HD>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (dev < 16) attr[dev] = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  CKR(smem_attr_once(kern, AttnCoCfg<HD>::SMEM_BYTES, attr, true));
   dim3 grid((p.S + ATT_BM - 1) / ATT_BM, p.NH, p.B);
   CK(launch_k(kern, grid, dim3(ATT_CO_THREADS), AttnCoCfg<HD>::SMEM_BYTES, st, tq, tk, tv, p));
   return B2_OK;
@@ -285,11 +288,13 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
                         cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   AttnParams p = p_in;
-  if (const char* ev = getenv("B2_V_LBO")) p.v_lbo = atoi(ev);   // bring-up knobs for the MN-major V descriptor
+#ifdef B2_DIAG   // bring-up / tracing knobs (tools/gpu_diag.py): compiled out of the product library
+  if (const char* ev = getenv("B2_V_LBO")) p.v_lbo = atoi(ev);   // MN-major V descriptor overrides
   if (const char* ev = getenv("B2_V_SBO")) p.v_sbo = atoi(ev);
   if (const char* ev = getenv("B2_ATT_CTATRACE")) p.cta_trace = reinterpret_cast<unsigned long long*>(strtoull(ev, nullptr, 0));
-  if (const char* ev = getenv("B2_ATT_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(ev, nullptr, 0));   // device pointer (diagnostics)
-  static const bool force_single = getenv("B2_ATTN_SINGLE") != nullptr;
+  if (const char* ev = getenv("B2_ATT_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(ev, nullptr, 0));   // device pointer
+#endif
+  static const bool force_single = getenv("B2_ATTN_SINGLE") != nullptr;   // read once
   const bool precise = p.q_lo_col != 0;
   const bool co = !precise && !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
   const int planes = precise ? 2 : 1;
@@ -318,7 +323,7 @@ static int decode_splits(int B, int NKV, int Tmax) {
   if (Tmax <= min_t) return 0;
   const int tiles = (Tmax + 63) / 64;
   int ns = (tiles + 7) / 8;
-  const int want = (2 * 148 + B * NKV - 1) / (B * NKV);
+  const int want = (2 * num_sms() + B * NKV - 1) / (B * NKV);
   if (ns < want) ns = want;
   if (ns > tiles) ns = tiles;
   if (ns > DEC_MAX_SPLITS) ns = DEC_MAX_SPLITS;
@@ -331,13 +336,8 @@ static int launch_decode_split(const bf16* q, int ldq, const bf16* kc, const bf1
                                int nrep, int Tmax, const int* t0_ptr, float scale, float softcap, int window, float* part,
                                int* cnt, int nsplit, cudaStream_t st) {
   auto kern = attn_decode_split_kernel<HD>;
-  static bool attr[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 16 || !attr[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DecSplitCfg<HD>::SMEM_BYTES));
-    if (dev < 16) attr[dev] = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  CKR(smem_attr_once(kern, DecSplitCfg<HD>::SMEM_BYTES, attr));
   CUtensorMap tk, tv;
   const uint64_t kv_rows = static_cast<uint64_t>(B) * NKV * Tmax;
   CKR(make_tmap(&tk, kc, kv_rows, HD, HD, 64));
@@ -443,6 +443,7 @@ struct Layer {
 
 struct b2_cache {
   b2_engine* e;
+  uint64_t uid;   // never reused (heap addresses are): keys the captured decode graphs
   int max_batch, max_tokens, len;
   bf16* kv;      // [L][2][max_batch][NKV][max_tokens][HD]
   int* t0_dev;
@@ -454,12 +455,19 @@ struct b2_cache {
 };
 
 struct GraphKey {
-  const void *ids, *logits, *cache;
+  const void *ids, *logits;
+  uint64_t cache_uid;
   int B, mode;
   bool operator<(const GraphKey& o) const {
-    return std::tie(ids, logits, cache, B, mode) < std::tie(o.ids, o.logits, o.cache, o.B, o.mode);
+    return std::tie(ids, logits, cache_uid, B, mode) < std::tie(o.ids, o.logits, o.cache_uid, o.B, o.mode);
   }
 };
+struct GraphEntry {
+  cudaGraphExec_t exec;
+  int64_t kernels;                       // kernel nodes in the graph (for the launch counter)
+  std::list<GraphKey>::iterator lru;     // position in b2_engine::graph_lru (front = most recently used)
+};
+constexpr size_t MAX_GRAPHS = 32;        // callers that pass fresh ids/logits buffers every step would otherwise grow the map
 
 struct b2_engine {
   b2_config cfg;
@@ -483,27 +491,38 @@ struct b2_engine {
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, bool>, CUtensorMap> tmaps;
   Stats st;
   bool decode_graph = false;
-  std::map<GraphKey, cudaGraphExec_t> graphs;
-  std::map<GraphKey, int64_t> graph_kernels;   // kernel nodes per captured graph (for the launch counter)
+  std::map<GraphKey, GraphEntry> graphs;
+  std::list<GraphKey> graph_lru;
   bool capturing = false;
+  std::vector<b2_cache*> caches;         // live caches created on this engine (orphaned, not freed, by b2_engine_destroy)
+  std::vector<uint8_t> sliding;          // per layer: 1 = sliding-window layer (HF layer_types); default: even layers
+  int n_sms = 148;
 };
 
+static void drop_graph(b2_engine* e, std::map<GraphKey, GraphEntry>::iterator it) {
+  cudaGraphExecDestroy(it->second.exec);
+  e->graph_lru.erase(it->second.lru);
+  e->graphs.erase(it);
+}
+
+// Descriptor cache.  The descriptor is returned BY VALUE: the map may be cleared (caller-provided output pointers keep
+// changing in long-running processes) while a caller still holds descriptors from earlier lookups of the same launch.
 static int get_tmap(b2_engine* e, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                    const CUtensorMap** out, bool f32 = false) {
+                    CUtensorMap* out, bool f32 = false) {
   auto key = std::make_tuple(ptr, rows, cols, ld, box_rows, f32);
   auto it = e->tmaps.find(key);
   if (it == e->tmaps.end()) {
-    if (e->tmaps.size() > 4096) e->tmaps.clear();   // caller-provided output pointers may keep changing
+    if (e->tmaps.size() > 4096) e->tmaps.clear();
     CUtensorMap m;
     CKR(make_tmap_t(&m, ptr, rows, cols, ld, box_rows, f32));
     it = e->tmaps.emplace(key, m).first;
   }
-  *out = &it->second;
+  *out = it->second;
   return B2_OK;
 }
 
 static void time_begin(b2_engine* e, cudaStream_t st, double flops, int kind) {
-  if (!e->st.timing || e->capturing) return;
+  if (!e->st.sample || e->capturing) return;
   Stats::Ev ev;
   if (!e->st.pool.empty()) {
     ev.a = e->st.pool.back().first;
@@ -519,7 +538,7 @@ static void time_begin(b2_engine* e, cudaStream_t st, double flops, int kind) {
   e->st.used.push_back(ev);
 }
 static void time_end(b2_engine* e, cudaStream_t st) {
-  if (!e->st.timing || e->capturing) return;
+  if (!e->st.sample || e->capturing) return;
   cudaEventRecord(e->st.used.back().b, st);
 }
 
@@ -533,7 +552,7 @@ static int pick_band(int N, int K) {
 // C = A . W^T through the engine (cached descriptors, stats)
 static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* a, int lda, const bf16* w, GemmParams p,
                     int a_rows = 0, int c_rows = 0) {
-  const CUtensorMap *ta, *tb, *tc;
+  CUtensorMap ta, tb, tc;
   if (e->cfg.precise) {   // A rows are [hi | lo]: contraction runs over 2K with the W k-coordinate wrapping at K
     p.K = 2 * p.k_wrap;
     lda *= 2;
@@ -552,7 +571,7 @@ static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* 
   if (epi == EPI_F32 || epi == EPI_RESID) CKR(get_tmap(e, p.out, c_rows ? c_rows : p.M, p.N, p.ldo, 32, &tc, true));
   p.band_m = pick_band(p.N, p.k_wrap);
   time_begin(e, st, 2.0 * p.M * static_cast<double>(p.N) * p.K, 0);
-  int r = two_cta ? launch_gemm2(epi, *ta, *tb, *tc, p, st) : launch_gemm(bn, epi, *ta, *tb, *tc, p, st);
+  int r = two_cta ? launch_gemm2(epi, ta, tb, tc, p, st) : launch_gemm(bn, epi, ta, tb, tc, p, st);
   time_end(e, st);
   e->st.launches++;
   e->st.gemm_launches++;
@@ -617,6 +636,9 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
   b2_engine* e = new b2_engine();
   e->cfg = c;
   e->device = device;
+  e->n_sms = num_sms();
+  e->sliding.assign(c.num_hidden_layers, 0);
+  for (int i = 0; i < c.num_hidden_layers; i += 2) e->sliding[i] = 1;   // HF Gemma-2 default layer_types: even layers slide
   const int rc = engine_alloc(e);
   if (rc != B2_OK) {                  // e.g. out of memory: free whatever was allocated
     b2_engine_destroy(e);
@@ -633,12 +655,24 @@ static void free_ws(b2_engine* e) {
   e->xn = e->q = e->att = e->hb = e->xnl = nullptr;
   e->ids_ws = nullptr;
   e->tmaps.clear();
-  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);   // graphs bake workspace pointers in
   e->graphs.clear();
+  e->graph_lru.clear();
 }
 
 extern "C" void b2_cache_destroy(b2_cache* c) {
   if (!c) return;
+  if (c->e) {   // graphs captured on this cache hold its (about to be freed) kv / t0 / scratch pointers
+    cudaSetDevice(c->e->device);
+    cudaDeviceSynchronize();
+    auto& live = c->e->caches;
+    for (size_t i = 0; i < live.size(); ++i)
+      if (live[i] == c) { live.erase(live.begin() + i); break; }
+    for (auto it = c->e->graphs.begin(); it != c->e->graphs.end();) {
+      auto cur = it++;
+      if (cur->first.cache_uid == c->uid) drop_graph(c->e, cur);
+    }
+  }
   cudaFree(c->kv);
   cudaFree(c->t0_dev);
   cudaFree(c->dec_part);
@@ -652,6 +686,7 @@ extern "C" void b2_engine_destroy(b2_engine* e) {
   cudaStreamSynchronize(e->stream);
   free_ws(e);
   if (e->scratch) b2_cache_destroy(e->scratch);
+  for (b2_cache* c : e->caches) c->e = nullptr;   // caches that outlive the engine (GC order) still free their own memory
   cudaFree(e->logits_ws);
   cudaFree(e->embed); cudaFree(e->g_final); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
   for (auto& L : e->layers) {
@@ -791,8 +826,10 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   if (max_tokens > e->cfg.max_positions)
     return fail(B2_ERR_ARG, "cache max_tokens %d exceeds the engine's RoPE table (%d positions)", max_tokens, e->cfg.max_positions);
   CK(cudaSetDevice(e->device));
+  static std::atomic<uint64_t> next_uid{1};
   b2_cache* c = new b2_cache();
   c->e = e;
+  c->uid = next_uid.fetch_add(1);
   c->max_batch = max_batch;
   c->max_tokens = max_tokens;
   c->len = 0;
@@ -819,12 +856,14 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
     b2_cache_destroy(c);
     return rc;
   }
+  e->caches.push_back(c);
   *out = c;
   return B2_OK;
 }
 extern "C" int b2_cache_len(const b2_cache* c) { return c ? c->len : fail(B2_ERR_ARG, "null cache"); }
 extern "C" int b2_cache_reset(b2_cache* c) {
   if (!c) return fail(B2_ERR_ARG, "null cache");
+  if (!c->e) return fail(B2_ERR_STATE, "the cache's engine has been destroyed");
   CK(cudaSetDevice(c->e->device));
   CK(cudaStreamSynchronize(c->e->stream));
   CK(cudaDeviceSynchronize());
@@ -837,10 +876,13 @@ static bf16* cache_k(const b2_cache* c, int layer) { return c->kv + (static_cast
 static bf16* cache_v(const b2_cache* c, int layer) { return c->kv + (static_cast<size_t>(layer) * 2 + 1) * c->pf * c->plane; }
 
 extern "C" int b2_cache_read(const b2_cache* c, int layer, int which, int batch, void* dev_out) {
+  if (c && !c->e) return fail(B2_ERR_STATE, "the cache's engine has been destroyed");
   if (!c || !dev_out || layer < 0 || layer >= c->e->cfg.num_hidden_layers || batch <= 0 || batch > c->max_batch)
     return fail(B2_ERR_ARG, "bad cache_read arguments");
   const b2_config& g = c->e->cfg;
   CK(cudaSetDevice(c->e->device));
+  if (c->len == 0) return B2_OK;                 // nothing cached: a zero-width copy is an error in CUDA
+  CK(cudaDeviceSynchronize());                   // forwards may still be running on non-blocking streams
   const bf16* src = which ? cache_v(c, layer) : cache_k(c, layer);
   // [batch*NKV] slabs of [len, HD] out of [max_tokens, HD]
   CK(cudaMemcpy2DAsync(dev_out, static_cast<size_t>(c->len) * g.head_dim * 2, src,
@@ -909,7 +951,7 @@ static int pick_split(int N, int K, int bn) {
   const int tiles = (N + bn - 1) / bn, kb = K / GEMM_BK;
   int best = 1;
   for (int sp = 2; sp <= MAX_SPLIT; sp *= 2)
-    if (kb % sp == 0 && kb / sp >= 8 && tiles * sp <= 148) best = sp;   // one wave: a second, partial wave costs more than it buys
+    if (kb % sp == 0 && kb / sp >= 8 && tiles * sp <= num_sms()) best = sp;   // one wave: a second, partial wave costs more than it buys
   return best;
 }
 
@@ -924,20 +966,37 @@ static int pick_bn(int M, int N, int min_bn) {
   return bn;
 }
 
-static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int64_t* ids, int B, int S, int logits_mode,
-                      float* logits, float* hidden) {
+struct FwdArgs {
+  const int64_t* ids = nullptr;     // [B,S] token ids, or
+  const float* embeds = nullptr;    // [B,S,H] fp32 inputs_embeds (llama3.2_model_numpy.py:645-676)
+  const int* pos_ids = nullptr;     // [S] RoPE positions (:657); nullptr = cache length + s
+  int B = 0, S = 0, logits_mode = 0;
+  float* logits = nullptr;
+  float* hidden = nullptr;          // [L+1,B,S,H]
+  float* attn_probs = nullptr;      // [L,B,NH,S,T] opt-in materialisation of the reference's `attentions` (:713-714)
+};
+
+static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdArgs& fa) {
   const b2_config& c = e->cfg;
+  const int B = fa.B, S = fa.S, logits_mode = fa.logits_mode;
+  float* const logits = fa.logits;
+  float* const hidden = fa.hidden;
   const int M = B * S, H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, HD = c.head_dim;
   const bool decode = (S == 1);
   const int pf = c.precise ? 2 : 1;            // bf16 activation rows are [hi | lo] in precise mode
   const bool skinny = M <= 128 && !hidden;     // few rows: split-K so the weight stream covers all SMs
   int pend = 0;                                // split-K partials of the last down_proj not yet folded into x
   const float escale = c.gemma ? sqrtf(static_cast<float>(H)) : 1.0f;
-  CK(launch_k(embed_kernel, dim3((M + 7) / 8), dim3(256), 0, st, reinterpret_cast<const long long*>(ids),
-              static_cast<const bf16*>(e->embed), e->x, M, H, c.vocab_size, escale));
+  if (fa.embeds) {   // hidden_states = inputs_embeds (* sqrt(H) for Gemma-2, gemma2_model.py:738-739)
+    CK(launch_k(scale_copy_kernel, dim3(2 * e->n_sms), dim3(256), 0, st, fa.embeds, e->x, static_cast<size_t>(M) * H / 4, escale));
+  } else {
+    CK(launch_k(embed_kernel, dim3((M + 7) / 8), dim3(256), 0, st, reinterpret_cast<const long long*>(fa.ids),
+                static_cast<const bf16*>(e->embed), e->x, M, H, c.vocab_size, escale));
+  }
   e->st.launches++;
   const int causal = (c.always_causal || S > 2) ? 1 : 0;   // llama3.2_model_numpy.py:479
   const float scale = c.attn_scale > 0.f ? c.attn_scale : 1.0f / sqrtf(static_cast<float>(HD));
+  const int T_total = cache->len + S;
   for (int li = 0; li < L; ++li) {
     Layer& Ly = e->layers[li];
     if (hidden) CK(cudaMemcpyAsync(hidden + static_cast<size_t>(li) * M * H, e->x, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
@@ -958,13 +1017,23 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
       p.k_cache = cache_k(cache, li);
       p.v_cache = cache_v(cache, li);
       p.t0_ptr = cache->t0_dev;
+      p.pos_ids = fa.pos_ids;
       p.rope_cos = e->rope_cos;
       p.rope_sin = e->rope_sin;
-      static const int qkv_bn = getenv("B2_QKV_BN") ? atoi(getenv("B2_QKV_BN")) : 0;   // bring-up knob
+      static const int qkv_bn = getenv("B2_QKV_BN") ? atoi(getenv("B2_QKV_BN")) : 0;   // bring-up knob, read once
       const int bn_qkv = (qkv_bn >= HD && M > 128) ? qkv_bn : pick_bn(M, p.N, HD);
       CKR(eng_gemm(e, st, bn_qkv, EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
     }
-    const int window = (c.sliding_window > 0 && (li % 2 == 0)) ? c.sliding_window : 0;
+    // HF Gemma-2: only the layers whose layer_types entry is "sliding_attention" slide (default pattern: even layers)
+    const int window = (c.sliding_window > 0 && e->sliding[li]) ? c.sliding_window : 0;
+    if (fa.attn_probs) {   // debug: this layer's [B,NH,S,T] softmax probabilities, recomputed from q and the K cache
+      const size_t rows = static_cast<size_t>(B) * c.num_attention_heads * S;
+      CK(launch_k(attn_probs_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, st, static_cast<const bf16*>(e->q),
+                  pf * e->q_cols, static_cast<const bf16*>(cache_k(cache, li)), fa.attn_probs + static_cast<size_t>(li) * rows * T_total,
+                  B, S, c.num_attention_heads, c.num_key_value_heads, HD, cache->max_tokens, static_cast<const int*>(cache->t0_dev),
+                  scale, c.attn_logit_softcap, causal, window));
+      e->st.launches++;
+    }
     if (decode) {
       CKR(attn_decode(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, pf * e->q_cols, B, c.num_attention_heads,
                       c.num_key_value_heads, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st,
@@ -1025,8 +1094,8 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
       GemmParams p = base_params(M, 2 * I, H);
       p.out = e->hb; p.ldo = pf * I; p.act = c.hidden_act;
       p.lo_off = c.precise ? I : 0;
-      // few rows: 128-wide tiles give exactly one wave of weight-streaming CTAs for the usual 2I / 128 <= 148
-      const int bn_glu = (M <= 128 && (2 * I) / 128 <= 148) ? 128 : pick_bn(M, 2 * I, 0);
+      // few rows: 128-wide tiles give exactly one wave of weight-streaming CTAs for the usual 2I / 128 <= #SMs
+      const int bn_glu = (M <= 128 && (2 * I) / 128 <= e->n_sms) ? 128 : pick_bn(M, 2 * I, 0);
       CKR(eng_gemm(e, st, bn_glu, EPI_GLU, e->xn, H, Ly.wgu, p));                          // act(gate)*up
     }
     if (!c.gemma) {
@@ -1092,17 +1161,22 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const int6
   return B2_OK;
 }
 
-extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int B, int S, int logits_mode,
-                          float* logits, float* hidden, void* stream) {
-  if (!e || !ids) return fail(B2_ERR_ARG, "null argument");
+extern "C" int b2_forward_ex(b2_engine* e, b2_cache* cache, const b2_forward_args* args) {
+  if (!e || !args) return fail(B2_ERR_ARG, "null argument");
+  const b2_forward_args& ua = *args;
+  if (!ua.ids && !ua.inputs_embeds) return fail(B2_ERR_ARG, "You have to specify either input_ids or inputs_embeds");
+  if (ua.ids && ua.inputs_embeds) return fail(B2_ERR_ARG, "You cannot specify both input_ids and inputs_embeds at the same time");
   if (!e->finalized) return fail(B2_ERR_STATE, "b2_finalize has not been called");
+  const int B = ua.B, S = ua.S, logits_mode = ua.logits_mode;
   if (B <= 0 || S <= 0) return fail(B2_ERR_ARG, "B and S must be positive");
-  if (logits_mode != B2_LOGITS_NONE && !logits) return fail(B2_ERR_ARG, "logits buffer is null");
+  if (logits_mode != B2_LOGITS_NONE && logits_mode != B2_LOGITS_ALL && logits_mode != B2_LOGITS_LAST)
+    return fail(B2_ERR_ARG, "bad logits_mode %d", logits_mode);
+  if (logits_mode != B2_LOGITS_NONE && !ua.logits) return fail(B2_ERR_ARG, "logits buffer is null");
   CK(cudaSetDevice(e->device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the CUDA (legacy) default stream
+  cudaStream_t st = static_cast<cudaStream_t>(ua.stream);   // NULL = the CUDA (legacy) default stream
   const b2_config& c = e->cfg;
   b2_cache* kc = cache;
-  if (!kc) {  // use_cache=False: attention over this call's tokens only
+  if (!kc) {  // no cache object: attention over this call's tokens only
     if (!e->scratch || e->scratch->max_batch < B || e->scratch->max_tokens < S) {
       if (e->scratch) { CK(cudaStreamSynchronize(st)); b2_cache_destroy(e->scratch); e->scratch = nullptr; }
       if (S > c.max_positions) return fail(B2_ERR_ARG, "sequence length %d exceeds max_positions %d", S, c.max_positions);
@@ -1112,6 +1186,7 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
     kc->len = 0;
     CK(cudaMemsetAsync(kc->t0_dev, 0, 4, st));
   } else {
+    if (kc->e != e) return fail(B2_ERR_ARG, "cache belongs to a different engine");
     if (B > kc->max_batch) return fail(B2_ERR_ARG, "batch %d exceeds the cache's max_batch %d", B, kc->max_batch);
     if (kc->len + S > kc->max_tokens)
       return fail(B2_ERR_ARG, "cache overflow: %d cached + %d new > max_tokens %d", kc->len, S, kc->max_tokens);
@@ -1123,14 +1198,23 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
                                 "is not supported by the reference path (set always_causal for chunked prefill)", S, kc->len);
   }
   CKR(ensure_ws(e, B * S, B));
+  FwdArgs fa;
+  fa.ids = ua.ids; fa.embeds = ua.inputs_embeds; fa.pos_ids = ua.position_ids;
+  fa.B = B; fa.S = S; fa.logits_mode = logits_mode; fa.logits = ua.logits; fa.hidden = ua.hidden; fa.attn_probs = ua.attn_probs;
+  // per-launch CUDA events on every st.every-th forward only: the other forwards take the plain launch path (events
+  // between launches defeat the programmatic-dependent-launch overlap)
+  e->st.sample = e->st.timing && (e->st.forwards % e->st.every == 0);
+  e->st.forwards++;
+  if (e->st.sample) e->st.timed_forwards++;
 
-  const bool use_graph = e->decode_graph && S == 1 && cache && !hidden && !e->st.timing;
+  const bool use_graph = e->decode_graph && S == 1 && cache && ua.ids && !ua.position_ids && !ua.hidden && !ua.attn_probs &&
+                         !e->st.sample;
   if (use_graph) {
-    GraphKey key{ids, logits, cache, B, logits_mode};
+    GraphKey key{ua.ids, ua.logits, cache->uid, B, logits_mode};
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
       // warm-up launch outside capture creates every descriptor / function attribute, then restore t0
-      CKR(run_layers(e, kc, st, ids, B, S, logits_mode, logits, nullptr));
+      CKR(run_layers(e, kc, st, fa));
       CK(launch_k(add_scalar_kernel, dim3(1), dim3(32), 0, st, kc->t0_dev, -S));
       CK(cudaStreamSynchronize(st));
       // the legacy default stream cannot be captured: record on the engine's own stream, replay on `st`
@@ -1139,7 +1223,7 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
       const int64_t launches_before = e->st.launches;
       e->capturing = true;
       CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      int r = run_layers(e, kc, cs, ids, B, S, logits_mode, logits, nullptr);
+      int r = run_layers(e, kc, cs, fa);
       cudaError_t ce = cudaStreamEndCapture(cs, &g);
       e->capturing = false;
       CKR(r);
@@ -1147,16 +1231,40 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
       cudaGraphExec_t ge;
       CK(cudaGraphInstantiate(&ge, g, 0));
       cudaGraphDestroy(g);
-      e->graph_kernels[key] = e->st.launches - launches_before;
+      const int64_t kernels = e->st.launches - launches_before;
       e->st.launches = launches_before;
-      it = e->graphs.emplace(key, ge).first;
+      if (e->graphs.size() >= MAX_GRAPHS) {   // evict the least recently used graph
+        CK(cudaStreamSynchronize(st));
+        drop_graph(e, e->graphs.find(e->graph_lru.back()));
+      }
+      e->graph_lru.push_front(key);
+      it = e->graphs.emplace(key, GraphEntry{ge, kernels, e->graph_lru.begin()}).first;
+    } else if (it->second.lru != e->graph_lru.begin()) {
+      e->graph_lru.splice(e->graph_lru.begin(), e->graph_lru, it->second.lru);
     }
-    CK(cudaGraphLaunch(it->second, st));
-    e->st.launches += e->graph_kernels[key];
+    CK(cudaGraphLaunch(it->second.exec, st));
+    e->st.launches += it->second.kernels;
   } else {
-    CKR(run_layers(e, kc, st, ids, B, S, logits_mode, logits, hidden));
+    CKR(run_layers(e, kc, st, fa));
   }
   if (cache) cache->len += S;
+  return B2_OK;
+}
+
+extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int B, int S, int logits_mode,
+                          float* logits, float* hidden, void* stream) {
+  if (!ids) return fail(B2_ERR_ARG, "null argument");
+  b2_forward_args a;
+  memset(&a, 0, sizeof(a));
+  a.ids = ids; a.B = B; a.S = S; a.logits_mode = logits_mode; a.logits = logits; a.hidden = hidden; a.stream = stream;
+  return b2_forward_ex(e, cache, &a);
+}
+
+extern "C" int b2_set_layer_types(b2_engine* e, const int32_t* is_sliding, int n) {
+  if (!e || !is_sliding) return fail(B2_ERR_ARG, "null argument");
+  if (n != e->cfg.num_hidden_layers) return fail(B2_ERR_ARG, "layer_types has %d entries, the model has %d layers", n, e->cfg.num_hidden_layers);
+  for (int i = 0; i < n; ++i) e->sliding[i] = is_sliding[i] ? 1 : 0;
+  for (auto it = e->graphs.begin(); it != e->graphs.end();) { auto cur = it++; drop_graph(e, cur); }   // windows are baked in
   return B2_OK;
 }
 
@@ -1233,7 +1341,10 @@ extern "C" int b2_sample_min_p(b2_engine* e, const float* logits, int B, int ld,
 // ------------------------------------------------------------------------------------------
 extern "C" int b2_set_timing(b2_engine* e, int on) {
   if (!e) return fail(B2_ERR_ARG, "null engine");
-  e->st.timing = on != 0;
+  e->st.timing = on > 0;       // on = k > 1: per-launch events on every k-th forward only
+  e->st.every = on > 1 ? on : 1;
+  e->st.sample = false;
+  e->st.forwards = 0;
   return B2_OK;
 }
 extern "C" int b2_reset_stats(b2_engine* e) {
@@ -1243,6 +1354,7 @@ extern "C" int b2_reset_stats(b2_engine* e) {
   for (auto& ev : e->st.used) e->st.pool.emplace_back(ev.a, ev.b);
   e->st.used.clear();
   e->st.launches = e->st.gemm_launches = e->st.attn_launches = 0;
+  e->st.forwards = e->st.timed_forwards = 0;
   return B2_OK;
 }
 extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
@@ -1252,6 +1364,7 @@ extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
   out->launches = e->st.launches;
   out->gemm_launches = e->st.gemm_launches;
   out->attn_launches = e->st.attn_launches;
+  out->timed_forwards = e->st.timed_forwards;
   if (!e->st.used.empty()) {
     CK(cudaDeviceSynchronize());
     for (auto& ev : e->st.used) {

@@ -46,6 +46,8 @@ struct GemmParams {
   __nv_bfloat16* k_cache;  // [B][NKV][Tmax][HD] (this layer)
   __nv_bfloat16* v_cache;
   const int* t0_ptr;       // device scalar: tokens already in the cache
+  const int* pos_ids;      // optional [S] caller position_ids for RoPE (llama3.2_model_numpy.py:657); nullptr = t0 + s.
+                           // The cache slot is always t0 + s.
   const float* rope_cos;   // [max_pos][HD/2]
   const float* rope_sin;
   int kv_lo_off;           // precise mode: element offset of the lo plane of the caches (0 = none)
@@ -186,9 +188,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
     const int half_chunks = HD >> 6;  // 32-column chunks per half head
     const int t0 = *p.t0_ptr;
     const int b = row / p.S, s = row - b * p.S;
-    const int pos = t0 + s;
-    const float* cosr = p.rope_cos + static_cast<size_t>(pos) * (HD >> 1);
-    const float* sinr = p.rope_sin + static_cast<size_t>(pos) * (HD >> 1);
+    const int pos = t0 + s;                                    // cache slot of this token
+    const int rpos = (p.pos_ids && row_ok) ? p.pos_ids[s] : pos;   // position the rotary table is read at
+    const float* cosr = p.rope_cos + static_cast<size_t>(rpos) * (HD >> 1);
+    const float* sinr = p.rope_sin + static_cast<size_t>(rpos) * (HD >> 1);
     // work items: (head hh, half-chunk i); this warp takes the items of its parity
     float4 cs4[8], sn4[8];   // cos/sin of this row's position for half-chunk tab_i (reused across the heads of a tile)
     int tab_i = -1;

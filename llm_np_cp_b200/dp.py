@@ -51,3 +51,50 @@ def gather_rows(local, world_rows: int, rank: int, world: int):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat([o[: e - b] for o, (b, e) in zip(out, sizes)], dim=0)
+
+
+class DataParallelLM:
+    """The multi-GPU product surface for the path that shards: one process per GPU (torchrun /
+    torch.distributed already initialised, or a single process), every rank holds a full replica of the weights and runs
+    its own engine on its contiguous slice of the batch; NO collective touches the data path.  The only communication is
+    the optional gather of the last-token logits, which is what generate()-style callers consume
+    (llama3.2_model_numpy.py:899).
+
+        dpm = DataParallelLM(model)                  # model: this rank's LlamaForCausalLM / Gemma2ForCausalLM
+        logits = dpm.prefill_last_logits(ids)        # ids: the GLOBAL [B,S] batch (same array on every rank)
+                                                     # -> [B,V] on every rank, rows in the global order
+    Every row equals what a single GPU computes for that sequence bit for bit (a sequence's result does not depend on its
+    batch neighbours; asserted by tests/test_gpu_model.py and tests/test_gpu_dp.py).
+    """
+
+    def __init__(self, model, rank: int = None, world: int = None):
+        import torch.distributed as dist
+        on = dist.is_available() and dist.is_initialized()
+        self.model = model
+        self.rank = rank if rank is not None else (dist.get_rank() if on else 0)
+        self.world = world if world is not None else (dist.get_world_size() if on else 1)
+
+    def local_rows(self, n_rows: int) -> Tuple[int, int]:
+        return shard_bounds(n_rows, self.rank, self.world)
+
+    def prefill_local(self, ids: np.ndarray, **kw):
+        """This rank's slice through model(...): returns the reference 5-tuple for the local rows (may be empty)."""
+        mine = shard_batch(np.asarray(ids), self.rank, self.world)
+        if mine.shape[0] == 0:
+            return None
+        return self.model(mine, **kw)
+
+    def prefill_last_logits(self, ids: np.ndarray, gather: bool = True):
+        """Last-position logits [B,V] of the global batch (gathered to every rank), or this rank's rows if not gather."""
+        import torch
+        from .model import LOGITS_LAST
+        ids = np.asarray(ids)
+        mine = shard_batch(ids, self.rank, self.world)
+        if mine.shape[0] > 0:
+            _, local, _, _, _ = self.model(mine, use_cache=False, output_hidden_states=False, output_attentions=False,
+                                           logits_mode=LOGITS_LAST)
+        else:
+            local = torch.empty((0, self.model.vocab_size), dtype=torch.float32, device=self.model.device)
+        if not gather:
+            return local
+        return gather_rows(local, ids.shape[0], self.rank, self.world)

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import B2Config, B2Stats, check
+from ._lib import B2Config, B2ForwardArgs, B2Stats, check
 
 LOGITS_NONE, LOGITS_ALL, LOGITS_LAST, LOGITS_ALL_LAST_TO_HOST = 0, 1, 2, 3
 
@@ -47,10 +47,39 @@ _DTYPES = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}
 
 
 def _cfg_get(config, key, default=None):
+    """Optional config field: dict-style configs (AttributeDict raises KeyError from __getattr__, so getattr's default
+    would never apply) and attribute-style ones (transformers configs) alike."""
+    if isinstance(config, dict):
+        return config.get(key, default)
     try:
-        return config[key]
-    except (KeyError, TypeError):
-        return getattr(config, key, default)
+        return getattr(config, key)
+    except (AttributeError, KeyError):
+        return default
+
+
+class _LayerViews:
+    """List-like view of the cache: ``cache.key_cache[i]`` copies only layer i off the engine's buffer (the
+    reference's ``key_cache`` is a plain list of per-layer arrays, llama3.2_model_numpy.py:313-314)."""
+
+    def __init__(self, cache, which):
+        self._c, self._which = cache, which
+
+    def __len__(self):
+        c = self._c
+        return 0 if c._h is None or c.num_items() == 0 else c._model._cfg.num_hidden_layers
+
+    def __getitem__(self, i):
+        n = len(self)
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(n))]
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("list index out of range")
+        return self._c._read_layer(self._which, i)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
 
 
 class KVCache:
@@ -81,27 +110,22 @@ class KVCache:
         if self._h is not None:
             check(_lib.lib().b2_cache_reset(self._h))
 
-    def _read(self, which, batch=None):
-        if self._h is None or self.num_items() == 0:
-            return []
+    def _read_layer(self, which, li, batch=None):
         m = self._model
         B = batch or self.max_batch
-        out = []
-        for li in range(m._cfg.num_hidden_layers):
-            t = torch.empty((B, m._cfg.num_key_value_heads, self.num_items(), m._cfg.head_dim),
-                            dtype=torch.bfloat16, device=m.device)
-            check(_lib.lib().b2_cache_read(self._h, li, which, B, t.data_ptr()))
-            out.append(t)
-        return out
+        t = torch.empty((B, m._cfg.num_key_value_heads, self.num_items(), m._cfg.head_dim),
+                        dtype=torch.bfloat16, device=m.device)
+        check(_lib.lib().b2_cache_read(self._h, li, which, B, t.data_ptr()))
+        return t
 
     @property
     def key_cache(self):
-        """list of [B,NKV,T,HD] post-RoPE keys, one per layer (bf16 device tensors)."""
-        return self._read(0)
+        """list-like of [B,NKV,T,HD] post-RoPE keys, one per layer (bf16 device tensors), read lazily per layer."""
+        return _LayerViews(self, 0)
 
     @property
     def value_cache(self):
-        return self._read(1)
+        return _LayerViews(self, 1)
 
     def __del__(self):
         try:
@@ -167,6 +191,8 @@ class _CausalLM:
         h = C.c_void_p()
         check(L.b2_engine_create(C.byref(c), device, C.byref(h)))
         self._h = h
+        self._graph_on = False
+        self._step_logits, self._step_ids = {}, {}
         src = weights_dict if weights_dict is not None else weights
         self._load(src)
         check(L.b2_finalize(self._h))
@@ -185,50 +211,103 @@ class _CausalLM:
             check(L.b2_load_weight(self._h, name.encode(), t.data_ptr(), shape, t.dim(), _DTYPES[t.dtype]))
 
     # ---- the reference's __call__ (llama3.2_model_numpy.py:777-830 / gemma2_model.py:830-886)
+    # opt-in: also materialise the reference's `attentions` tuple (L tensors [B,NH,S,T], llama3.2_model_numpy.py:713-714)
+    # through a separate debug kernel.  Off by default: the fused attention never forms the score matrix, and at
+    # Llama-1B S=2048 the tuple alone is 8.6 GB.
+    materialize_attentions = False
+
     def __call__(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, labels=None,
                  use_cache=None, output_attentions=True, output_hidden_states=True, return_dict=True, kv_cache=None,
                  logits_mode: int = LOGITS_ALL, logits_out=None):
         if input_ids is not None and inputs_embeds is not None:
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
-        if input_ids is None:
-            if inputs_embeds is not None:
-                raise NotImplementedError("inputs_embeds is not supported by the B200 engine")
+        if input_ids is None and inputs_embeds is None:
             raise ValueError("You have to specify either input_ids or inputs_embeds")
         use_cache = use_cache if use_cache is not None else _cfg_get(self.config, "use_cache", False)
-        ids = input_ids
-        if isinstance(ids, np.ndarray):
-            ids = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64))
-        ids = torch.as_tensor(ids, dtype=torch.int64)
-        if ids.dim() != 2:
-            raise ValueError("input_ids must be [batch, seq]")
-        if ids.device.type != "cuda":
-            if int(ids.min()) < 0 or int(ids.max()) >= self.vocab_size:
-                raise IndexError("token id out of range")      # NumPy fancy indexing raises the same (:675)
-            ids = ids.to(self.device, non_blocking=True)
-        ids = ids.contiguous()
-        B, S = ids.shape
-        cache_h = None
-        if use_cache and kv_cache is not None:
-            cache_h = kv_cache._bind(self, B)
         H, V, Lc = self._cfg.hidden_size, self._cfg.vocab_size, self._cfg.num_hidden_layers
-        logits = hidden = None
+        ids = emb = None
+        if input_ids is not None:
+            ids = input_ids
+            if isinstance(ids, np.ndarray):
+                ids = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64))
+            ids = torch.as_tensor(ids, dtype=torch.int64)
+            if ids.dim() != 2:
+                raise ValueError("input_ids must be [batch, seq]")
+            if ids.device.type != "cuda":
+                if int(ids.min()) < 0 or int(ids.max()) >= self.vocab_size:
+                    raise IndexError("token id out of range")      # NumPy fancy indexing raises the same (:675)
+                ids = ids.to(self.device, non_blocking=True)
+            ids = ids.contiguous()
+            B, S = ids.shape
+        else:                                                      # caller-provided embeddings (:645-652, :675-676)
+            emb = inputs_embeds
+            if isinstance(emb, np.ndarray):
+                emb = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32))
+            emb = torch.as_tensor(emb, dtype=torch.float32).to(self.device).contiguous()
+            if emb.dim() != 3 or emb.shape[-1] != H:
+                raise ValueError(f"inputs_embeds must be [batch, seq, {H}]")
+            B, S = emb.shape[:2]
+        # The reference appends to kv_cache whenever one is passed; use_cache only decides whether RoPE positions
+        # continue from the cache length (:659-672).  Caller position_ids win over both (:657).
+        cache_h = kv_cache._bind(self, B) if kv_cache is not None else None
+        pos = None
+        if position_ids is not None:
+            pos = torch.as_tensor(np.asarray(position_ids.cpu() if torch.is_tensor(position_ids) else position_ids)).reshape(-1)
+            if pos.numel() != S:
+                raise ValueError("position_ids must be [1, seq] (shared by the batch, like the reference's)")
+        elif kv_cache is not None and not use_cache and kv_cache.num_items() > 0:
+            pos = torch.arange(0, S)
+        if pos is not None:
+            if int(pos.min()) < 0 or int(pos.max()) >= self._cfg.max_positions:
+                raise IndexError("position id outside the engine's RoPE table")
+            pos = pos.to(torch.int32).to(self.device)
+        graph_step = (self._graph_on and S == 1 and cache_h is not None and ids is not None and pos is None
+                      and not output_hidden_states and logits_mode != LOGITS_NONE)
+        logits = hidden = probs = None
         if logits_mode != LOGITS_NONE:
             shape = (B, S, V) if logits_mode == LOGITS_ALL else (B, V)
             if logits_out is not None:           # caller-owned buffer (stable pointer: lets decode steps replay one CUDA graph)
                 if tuple(logits_out.shape) != shape or logits_out.dtype != torch.float32 or not logits_out.is_contiguous():
                     raise ValueError(f"logits_out must be a contiguous float32 tensor of shape {shape}")
                 logits = logits_out
+            elif graph_step:                     # engine-side graphs are keyed on pointers: reuse one buffer per (cache, B, mode)
+                key = (id(kv_cache), B, logits_mode)
+                logits = self._step_logits.get(key)
+                if logits is None:
+                    if len(self._step_logits) >= 8:
+                        self._step_logits.clear(); self._step_ids.clear()
+                    logits = self._step_logits[key] = torch.empty(shape, dtype=torch.float32, device=self.device)
             else:
                 logits = torch.empty(shape, dtype=torch.float32, device=self.device)
+        if graph_step:                           # same for the one-token id buffer
+            key = (id(kv_cache), B)
+            buf = self._step_ids.get(key)
+            if buf is None:
+                buf = self._step_ids[key] = torch.empty((B, 1), dtype=torch.int64, device=self.device)
+            if buf.data_ptr() != ids.data_ptr():
+                buf.copy_(ids)
+                ids = buf
         if output_hidden_states:
             hidden = torch.empty((Lc + 1, B, S, H), dtype=torch.float32, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        check(_lib.lib().b2_forward(self._h, cache_h, ids.data_ptr(), B, S, logits_mode,
-                                    logits.data_ptr() if logits is not None else None,
-                                    hidden.data_ptr() if hidden is not None else None, stream))
-        self._keep = ids                                       # keep inputs alive until the stream is done
+        T = (kv_cache.num_items() if kv_cache is not None else 0) + S
+        if output_attentions and self.materialize_attentions:
+            probs = torch.empty((Lc, B, self._cfg.num_attention_heads, S, T), dtype=torch.float32, device=self.device)
+        a = B2ForwardArgs()
+        a.ids = ids.data_ptr() if ids is not None else None
+        a.inputs_embeds = emb.data_ptr() if emb is not None else None
+        a.position_ids = pos.data_ptr() if pos is not None else None
+        a.B, a.S, a.logits_mode = B, S, logits_mode
+        a.logits = logits.data_ptr() if logits is not None else None
+        a.hidden = hidden.data_ptr() if hidden is not None else None
+        a.attn_probs = probs.data_ptr() if probs is not None else None
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(_lib.lib().b2_forward_ex(self._h, cache_h, C.byref(a)))
+        self._keep = (ids, emb, pos)                           # keep inputs alive until the stream is done
+        if graph_step and logits_out is None:
+            logits = logits.clone()                            # the step buffer is overwritten by the next replay
         hs = tuple(hidden[i] for i in range(Lc + 1)) if hidden is not None else None
-        return (None, logits, kv_cache, hs, None)
+        att = tuple(probs[i] for i in range(Lc)) if probs is not None else None
+        return (None, logits, kv_cache, hs, att)
 
     def argmax(self, logits, out=None):
         """Greedy pick on the device: [B,V] fp32 logits -> [B] int64 (np.argmax semantics)."""
@@ -241,11 +320,20 @@ class _CausalLM:
         return out
 
     # ---- instrumentation
-    def set_timing(self, on: bool):
-        check(_lib.lib().b2_set_timing(self._h, 1 if on else 0))
+    def set_timing(self, on):
+        """True/1: CUDA events around every GEMM / attention launch; k > 1: only on every k-th forward; False/0: off."""
+        check(_lib.lib().b2_set_timing(self._h, int(on)))
 
     def set_decode_graph(self, on: bool):
+        self._graph_on = bool(on)
         check(_lib.lib().b2_set_decode_graph(self._h, 1 if on else 0))
+
+    def set_layer_types(self, layer_types):
+        """HF ``config.layer_types`` ("sliding_attention" / "full_attention" per layer, or booleans): which layers
+        apply the sliding window.  Without this call the engine uses transformers' Gemma-2 default (even layers)."""
+        flags = [1 if (t == "sliding_attention" or t is True or t == 1) else 0 for t in layer_types]
+        arr = (C.c_int32 * len(flags))(*flags)
+        check(_lib.lib().b2_set_layer_types(self._h, arr, len(flags)))
 
     def reset_stats(self):
         check(_lib.lib().b2_reset_stats(self._h))
@@ -295,6 +383,9 @@ class Gemma2ForCausalLM(_CausalLM):
             kw.setdefault("use_query_pre_attn_scalar", True)
             kw.setdefault("always_causal", True)
         super().__init__(config, weights_dict, device, max_positions, **kw)
+        lt = _cfg_get(config, "layer_types", None)
+        if hf_flags and lt:
+            self.set_layer_types(lt)
 
 
 # the reference's class names, for drop-in imports

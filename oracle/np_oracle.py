@@ -142,6 +142,30 @@ def to_numpy_f32(weights) -> Dict[str, np.ndarray]:
 # --------------------------------------------------------------------------------------
 # array ops (L0)
 # --------------------------------------------------------------------------------------
+# Parity tests at the benchmarked shapes run hundreds of one-token steps over GB-sized weights: casting W to the
+# activation dtype (float64 after the first attention, App. B Q5) on every call would dominate.  Opt-in cache of the
+# cast copies, keyed by the weight array's identity; same values, so results are unchanged.
+_CAST_CACHE: Dict[tuple, np.ndarray] = {}
+CACHE_CASTS = False
+BY_HEAD_MIN_ELEMS = 1 << 26      # score-matrix size above which attention() evaluates head by head (same arithmetic)
+
+
+def clear_cast_cache():
+    _CAST_CACHE.clear()
+
+
+def _cast(w, dtype):
+    if w.dtype == dtype:
+        return w
+    if not CACHE_CASTS:
+        return w.astype(dtype)
+    key = (id(w), np.dtype(dtype).str)
+    hit = _CAST_CACHE.get(key)
+    if hit is None:
+        hit = _CAST_CACHE[key] = w.astype(dtype)
+    return hit
+
+
 def linear(x, w, faithful: bool):
     """y = x . W^T with W stored [out, in]; no bias is ever loaded.
     Reference: Linear_np.__call__, llama3.2_model_numpy.py:134-144 -- an N-D ``np.dot`` into a
@@ -153,7 +177,7 @@ def linear(x, w, faithful: bool):
         np.dot(x, w.T, out=out)
         return out
     x2 = x.reshape(-1, x.shape[-1])
-    y = x2 @ w.T.astype(x.dtype, copy=False)
+    y = x2 @ _cast(w, x.dtype).T
     return y.reshape(*x.shape[:-1], w.shape[0])
 
 
@@ -280,13 +304,82 @@ class Extras:
     behaviour (off)."""
     attn_softcap: Optional[float] = None       # tanh(s/cap)*cap after scaling, before the mask
     sliding_window: Optional[int] = None       # kv_idx > q_idx - window on "sliding" layers
-    sliding_layers: str = "even"               # HF default pattern: even layers slide
+    sliding_layers: object = "even"            # HF default layer_types pattern: even layers slide; or a per-layer list of
+                                               # booleans / "sliding_attention" strings (config.layer_types)
     attn_scale: Optional[float] = None         # e.g. query_pre_attn_scalar ** -0.5
     always_causal: bool = False                # drop the q_len > 2 quirk
     rope_scaling: Optional[dict] = None        # HF llama3 frequency scaling {factor, low_freq_factor, high_freq_factor, original_max_position_embeddings}
 
 
-def attention(cfg, W, li, x, cos, sin, cache, faithful, stable_softmax, ex: Extras):
+def _slides(ex: Extras, li: int) -> bool:
+    """Does layer li apply the sliding window?  (transformers modeling_gemma2: config.layer_types[li] ==
+    "sliding_attention"; default pattern = even layers.)"""
+    if ex.sliding_window is None:
+        return False
+    if isinstance(ex.sliding_layers, str):
+        return (li % 2 == 0) if ex.sliding_layers == "even" else True
+    t = ex.sliding_layers[li]
+    return t == "sliding_attention" or t is True or t == 1
+
+
+def _keep_mask(S, T, li, ex: Extras):
+    """Boolean [S,T] keep-mask of the score matrix, or None when the reference applies no mask (q_len <= 2,
+    llama3.2_model_numpy.py:479).  Same predicate as the in-line code of attention() below."""
+    if not (S > 2 or ex.always_causal):
+        return None
+    if ex.always_causal or ex.sliding_window is not None:
+        qi = np.arange(T - S, T)[:, None]
+        ki = np.arange(T)[None, :]
+        keep = ki <= qi
+        if _slides(ex, li):
+            keep &= ki > qi - ex.sliding_window
+        return keep
+    if S != T:   # the reference's [q,q] tril cannot broadcast onto [q,kv] (App. B Q4)
+        raise ValueError(f"operands could not be broadcast together with shapes (1,1,{S},{S}) () (B,NH,{S},{T})")
+    return np.tril(np.ones((S, S), dtype=np.float32)) != 0
+
+
+def _attention_core_by_head(q, k, v, n_rep, HD, S, T, li, stable_softmax, ex: Extras, keep_attn):
+    """scores -> mask -> softmax -> P.V of attention(), evaluated one query head at a time on a small thread pool
+    with in-place ufuncs (NumPy releases the GIL inside them).  Exactly the per-element arithmetic of the block
+    below -- repeat_kv becomes head indexing (kv head = q head // n_rep, :188-204), np.where becomes a masked
+    assignment -- so long sequences (S = 8192: 12.9 GB of float64 scores per layer otherwise) stay tractable for
+    the parity tests at the benchmarked shapes."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    B, NH = q.shape[0], q.shape[1]
+    keep = _keep_mask(S, T, li, ex)
+    drop = None if keep is None else ~keep
+    out = np.empty((B, NH, S, HD), dtype=np.float32 if stable_softmax else np.float64)
+    probs = np.empty((B, NH, S, T), dtype=out.dtype) if keep_attn else None
+
+    def one(h):
+        kh, vh = k[:, h // n_rep], v[:, h // n_rep]
+        if ex.attn_scale is None:
+            s = np.matmul(q[:, h], kh.transpose(0, 2, 1)) / np.sqrt(HD)          # float64 under NumPy 2 (:475-477)
+        else:
+            s = np.matmul(q[:, h], kh.transpose(0, 2, 1)) * np.float64(ex.attn_scale)
+        if ex.attn_softcap is not None:
+            s /= ex.attn_softcap
+            np.tanh(s, out=s)
+            s *= ex.attn_softcap
+        if drop is not None:
+            s[:, drop] = float("-inf")
+        if stable_softmax:                                                       # CuPy twin: fp32, max-subtracted
+            s = s.astype(np.float32)
+            s -= np.max(s, axis=-1, keepdims=True)
+        np.exp(s, out=s)
+        s /= np.sum(s, axis=-1, keepdims=True)
+        out[:, h] = np.matmul(s, vh)
+        if probs is not None:
+            probs[:, h] = s
+
+    with ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 1) // 4))) as pool:
+        list(pool.map(one, range(NH)))
+    return out, probs
+
+
+def attention(cfg, W, li, x, cos, sin, cache, faithful, stable_softmax, ex: Extras, keep_attn: bool = False):
     """LlamaAttention.__call__ (llama3.2_model_numpy.py:407-516) / Gemma2Attention
     (gemma2_model.py:480-582)."""
     B, S, _ = x.shape
@@ -299,6 +392,9 @@ def attention(cfg, W, li, x, cos, sin, cache, faithful, stable_softmax, ex: Extr
     if cache is not None:
         k, v = cache.update(k, v, li)
     T = k.shape[-2]
+    if not faithful and B * NH * S * T > BY_HEAD_MIN_ELEMS:
+        o, pr = _attention_core_by_head(q, k, v, NH // NKV, HD, S, T, li, stable_softmax, ex, keep_attn)
+        return linear(o.transpose(0, 2, 1, 3).reshape(B, S, NH * HD), W[p + "o_proj.weight"], faithful), pr
     kr, vr = repeat_kv(k, NH // NKV), repeat_kv(v, NH // NKV)
     if ex.attn_scale is None:
         # f32 / np.float64 scalar -> float64 under NumPy 2 (:475-477, App. B Q5)
@@ -314,9 +410,7 @@ def attention(cfg, W, li, x, cos, sin, cache, faithful, stable_softmax, ex: Extr
             qi = np.arange(T - S, T)[:, None]
             ki = np.arange(T)[None, :]
             keep = ki <= qi
-            slide = ex.sliding_window is not None and (
-                (li % 2 == 0) if ex.sliding_layers == "even" else True)
-            if slide:
+            if _slides(ex, li):
                 keep &= ki > qi - ex.sliding_window
             s = np.where(keep[None, None], s, float("-inf"))
         else:
@@ -345,7 +439,8 @@ class Output:
 
 def forward(cfg, W: Dict[str, np.ndarray], input_ids, cache: Optional[KVCache] = None, *,
             faithful: bool = False, keep_attn: bool = False,
-            extras: Optional[Extras] = None) -> Output:
+            extras: Optional[Extras] = None, logit_positions=None, inputs_embeds=None,
+            position_ids=None, use_cache: bool = True) -> Output:
     """model(input_ids) -> logits, L+1 hidden states (and optionally L attention maps).
 
     Llama: LlamaForCausalLM_np.__call__ -> LlamaModel.__call__ -> LlamaDecoderLayer.__call__
@@ -354,11 +449,17 @@ def forward(cfg, W: Dict[str, np.ndarray], input_ids, cache: Optional[KVCache] =
     GeGLU, final tanh soft-cap; stable fp32 softmax because that file is CuPy-only)."""
     ex = extras or Extras()
     gem = cfg.family == "gemma2"
-    ids = np.asarray(input_ids)
-    B, S = ids.shape
-    t0 = cache.num_items() if cache is not None else 0
-    pos = np.expand_dims(np.arange(t0, t0 + S, dtype=np.int64), 0)         # [1,S]  (:659-672)
-    x = W["model.embed_tokens.weight"][ids]                                # (:675)
+    if inputs_embeds is None:
+        ids = np.asarray(input_ids)
+        B, S = ids.shape
+    else:
+        B, S = inputs_embeds.shape[:2]
+    # positions continue from the cache only when use_cache is set (:659-672); the cache is appended to either way
+    t0 = cache.num_items() if (cache is not None and use_cache) else 0
+    pos = np.expand_dims(np.arange(t0, t0 + S, dtype=np.int64), 0)         # [1,S]
+    if position_ids is not None:
+        pos = np.asarray(position_ids, dtype=np.int64).reshape(1, S)       # caller positions win (:657)
+    x = W["model.embed_tokens.weight"][ids] if inputs_embeds is None else np.asarray(inputs_embeds)   # (:675-676)
     if gem:
         x = x * (cfg.hidden_size ** 0.5)                                   # gemma2_model.py:738-739
     hs, att = [], []
@@ -372,14 +473,14 @@ def forward(cfg, W: Dict[str, np.ndarray], input_ids, cache: Optional[KVCache] =
             # cos/sin are recomputed per layer in the activations' dtype (gemma2_model.py:506)
             h = rms_norm(x, W[p + "input_layernorm.weight"], cfg.rms_norm_eps, True)
             cos, sin = rope_tables(cfg.head_dim, cfg.rope_theta, pos, h.dtype, ex.rope_scaling)
-            a, pr = attention(cfg, W, li, h, cos, sin, cache, faithful, True, ex)
+            a, pr = attention(cfg, W, li, h, cos, sin, cache, faithful, True, ex, keep_attn)
             x = x + rms_norm(a, W[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps, True)
             h = rms_norm(x, W[p + "pre_feedforward_layernorm.weight"], cfg.rms_norm_eps, True)
             m = mlp(cfg, W, li, h, faithful)
             x = x + rms_norm(m, W[p + "post_feedforward_layernorm.weight"], cfg.rms_norm_eps, True)
         else:
             h = rms_norm(x, W[p + "input_layernorm.weight"], cfg.rms_norm_eps)
-            a, pr = attention(cfg, W, li, h, cos, sin, cache, faithful, False, ex)
+            a, pr = attention(cfg, W, li, h, cos, sin, cache, faithful, False, ex, keep_attn)
             x = x + a
             h = rms_norm(x, W[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
             x = x + mlp(cfg, W, li, h, faithful)
@@ -387,6 +488,8 @@ def forward(cfg, W: Dict[str, np.ndarray], input_ids, cache: Optional[KVCache] =
             att.append(pr)
     x = rms_norm(x, W["model.norm.weight"], cfg.rms_norm_eps, gem)
     hs.append(x)
+    if logit_positions is not None:        # the same lm_head product, evaluated at a subset of positions only
+        x = x[:, np.asarray(logit_positions), :]
     logits = linear(x, W["model.embed_tokens.weight"], faithful)           # tied lm_head (:1025-1026)
     cap = cfg.get("final_logit_softcapping") if gem else None
     if cap is not None:

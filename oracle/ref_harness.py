@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- run the UNMODIFIED reference modules in this container.
 
-/root/reference is read-only and absent on the GPU box, so this is used only here, by
-``oracle/make_golden.py``, to pin the restatement in ``np_oracle.py``.
-Nothing is copied: the reference files are exec'd from where they lie with their import-time
-side effects neutralised:
+/root/reference is read-only and absent on the GPU box.  Here (container) the reference files are exec'd from
+where they lie -- used by ``oracle/make_golden*.py`` to pin the restatement in ``np_oracle.py`` (SURVEY.md section
+8c).  On the GPU box the same modules are loaded from the byte-compiled artefacts ``oracle/_ref/*.pyc`` that
+``oracle/build_ref.py`` produced here (a build output, git-ignored; no reference source is copied), so that
+bench.py's CPU legs can time the reference's own classes.  Import-time side effects are neutralised:
 
 * ``huggingface_hub.notebook_login`` is stubbed (llama3.2_model_numpy.py:972-973 calls it);
 * ``gemma2_model.py`` is CuPy-only, so a fake ``cupy`` module (NumPy namespace + a RawKernel
@@ -13,13 +14,37 @@ side effects neutralised:
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
+import os
 import sys
 import types
 
 import numpy as np
 
 REF_DIR = "/root/reference"
+BUILT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def available() -> bool:
+    """Can the reference's Llama NumPy module be loaded here (source mounted, or oracle/_ref built)?"""
+    return os.path.exists(f"{REF_DIR}/llama3.2_model_numpy.py") or os.path.exists(f"{BUILT_DIR}/llama3_2_model_numpy.pyc")
+
+
+def _exec_reference(modname: str, src: str, built: str):
+    """Module object of reference file `src`: from /root/reference if mounted, else from its byte-compiled build."""
+    path = f"{REF_DIR}/{src}"
+    if os.path.exists(path):
+        spec = importlib.util.spec_from_file_location(modname, path)
+    else:
+        pyc = f"{BUILT_DIR}/{built}"
+        if not os.path.exists(pyc):
+            raise FileNotFoundError(f"neither {path} nor {pyc} exists (run oracle/build_ref.py where /root/reference is mounted)")
+        loader = importlib.machinery.SourcelessFileLoader(modname, pyc)
+        spec = importlib.util.spec_from_loader(modname, loader)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _stub_login():
@@ -30,10 +55,7 @@ def _stub_login():
 def load_llama_numpy():
     """-> the module object of /root/reference/llama3.2_model_numpy.py."""
     _stub_login()
-    spec = importlib.util.spec_from_file_location("ref_llama_np", f"{REF_DIR}/llama3.2_model_numpy.py")
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    return _exec_reference("ref_llama_np", "llama3.2_model_numpy.py", "llama3_2_model_numpy.pyc")
 
 
 class _FakeRawKernel:
@@ -61,9 +83,7 @@ def load_gemma2():
     fake.asnumpy = np.asarray
     sys.modules["cupy"] = fake
     try:
-        spec = importlib.util.spec_from_file_location("ref_gemma2", f"{REF_DIR}/gemma2_model.py")
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
+        mod = _exec_reference("ref_gemma2", "gemma2_model.py", "gemma2_model.pyc")
     finally:
         sys.modules.pop("cupy", None)
 

@@ -1,0 +1,211 @@
+"""GPU end-to-end parity AT THE BENCHMARKED SHAPES (BASELINE.json configs #2-#5): the engine runs the exact
+configuration bench.py times; the NumPy oracle (oracle/np_oracle.py, pinned to the reference by the golden fixtures)
+runs on the box's host cores for a subset of the batch rows -- sequences never interact (the batch axis is untouched by
+every op, llama3.2_model_numpy.py:418-429), so a row of the B-row engine batch must equal the oracle run on that row
+alone.  Rows are taken from both ends of the batch so a wrong row stride or a 32-bit overflow at M*V > 2^31 shows up.
+
+Depth is trimmed where the oracle's float64 CPU cost would not fit a test (configs #3/#4: widths, head_dim, vocabulary
+and sequence length are the real ones, the layer count is 2); configs #2 and #5 run all 16 layers.
+
+Stated tolerance of the fast path (bf16 tensor-core operands, fp32 everything else), relative to std(reference logits):
+MAX_REL / MEAN_REL below = ~1.5x the values measured on B200 and printed as "[parity]" lines.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import np_oracle as O
+import llm_np_cp_b200 as M
+from llm_np_cp_b200.model import LOGITS_ALL, LOGITS_LAST
+
+MAX_REL, MEAN_REL = 0.10, 0.018          # measured: max/std <= 0.066, mean/std <= 0.0115
+HID_REL = 0.06                           # hidden states: max-abs <= HID_REL * std(that hidden state) (+1e-3 abs)
+
+
+@pytest.fixture(autouse=True)
+def _oracle_big_mode(monkeypatch):
+    monkeypatch.setattr(O, "CACHE_CASTS", True)
+    yield
+    O.clear_cast_cache()
+    torch.cuda.empty_cache()
+
+
+def report(what, got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    d = np.abs(got - want)
+    std = want.std()
+    print(f"[parity] {what}: max_abs={d.max():.4g} mean_abs={d.mean():.4g} ref_std={std:.4g} "
+          f"max/std={d.max() / std:.4g} mean/std={d.mean() / std:.4g}", flush=True)
+    assert np.isfinite(got).all(), what
+    return d.max() / std, d.mean() / std
+
+
+def check_logits(what, got, want):
+    mx, mean = report(what, got, want)
+    assert mx <= MAX_REL and mean <= MEAN_REL, (what, mx, mean)
+    agree = float((np.asarray(got).argmax(-1) == np.asarray(want).argmax(-1)).mean())
+    print(f"[parity] {what}: argmax agreement {agree:.4f}", flush=True)
+    return agree
+
+
+def check_hidden(what, got_rows, want_list):
+    """got_rows: [L+1, rows, S, H] from the engine; want_list: oracle hidden states (list of [rows,S,H])."""
+    worst = 0.0
+    for i, w in enumerate(want_list):
+        g = got_rows[i].astype(np.float64)
+        d = np.abs(g - w).max()
+        s = w.std()
+        worst = max(worst, d / s)
+        assert d <= HID_REL * s + 1e-3, (what, i, d, s)
+    print(f"[parity] {what}: hidden states, worst max_abs/std over {len(want_list)} = {worst:.4g}", flush=True)
+
+
+def positions_for(S, n=16):
+    return sorted(set(list(range(0, S, max(1, S // n))) + [S - 1]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Llama-3.2-1B weights are shared by the config #2 and config #5 cases (generating 1.2 G random parameters takes ~20 s)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def llama1b():
+    cfg = O.llama_config("1b")
+    t = time.perf_counter()
+    w = O.synth_weights(cfg, seed=0, std=0.02)
+    wn = O.to_numpy_f32(w)
+    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, max_positions=2048)
+    print(f"[setup] llama-1b synthetic checkpoint + engine: {time.perf_counter() - t:.1f} s", flush=True)
+    yield cfg, wn, model
+    del model
+
+
+def test_config2_llama1b_b8_s2048_full_depth(llama1b):
+    """BASELINE config #2 exactly as bench.py runs it: B = 8 sequences x 2048 tokens, all 16 layers, full [B,S,V] fp32
+    logits (8.4 GB), 2-CTA GEMMs at M = 16384, co-resident attention over 16 kv tiles."""
+    cfg, wn, model = llama1b
+    B, S, V = 8, 2048, cfg.vocab_size
+    ids = np.random.default_rng(1234).integers(0, V, (B, S)).astype(np.int64)     # bench.py's ids for rank 0
+    rows, pos = [0, B - 1], positions_for(S)
+    _, logits, _, hs, _ = model(ids, use_cache=False, logits_mode=LOGITS_ALL)
+    got_lg = logits[rows][:, pos].cpu().numpy()
+    got_hs = torch.stack(hs)[:, rows].cpu().numpy()
+    del logits, hs
+    t = time.perf_counter()
+    want = O.forward(cfg, wn, ids[rows], logit_positions=pos)
+    print(f"[oracle] config #2 rows {rows}: {time.perf_counter() - t:.1f} s on {os.cpu_count()} cores", flush=True)
+    agree = check_logits(f"config#2 1B B=8 S=2048 L=16 logits rows {rows} x {len(pos)} positions", got_lg, want.logits)
+    assert agree >= 0.9
+    check_hidden("config#2", got_hs, want.hidden_states)
+
+
+def test_config5_llama1b_decode_b64_graph_128_steps(llama1b):
+    """BASELINE config #5: B = 64, 16-token prompt, 128 greedy steps replayed as one CUDA graph each, KV cache on the
+    device.  Four of the 64 sequences are followed by the oracle with its own KVCache (teacher-forced with the tokens the
+    engine picked): per-step logits within the fast-path tolerance, and the engine's pick must be the oracle's argmax
+    or within the stated error of it."""
+    cfg, wn, model = llama1b
+    B, P, NT, V = 64, 16, 128, cfg.vocab_size
+    rows = [0, 21, 42, 63]
+    prompt = np.random.default_rng(99).integers(0, V, (B, P)).astype(np.int64)
+    cache = M.KVCache(max_batch=B, max_tokens=P + NT)
+    model.set_decode_graph(True)
+    try:
+        dev = model.device
+        tok = torch.empty((B, 1), dtype=torch.int64, device=dev)
+        lg = torch.empty((B, V), dtype=torch.float32, device=dev)
+        _, l0, _, _, _ = model(prompt, use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=LOGITS_LAST)
+        step_logits = [l0[rows].clone()]
+        model.argmax(l0, out=tok.view(-1))
+        toks = [tok[rows, 0].clone()]
+        for _ in range(NT - 1):
+            model(tok, use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=LOGITS_LAST, logits_out=lg)
+            step_logits.append(lg[rows].clone())
+            model.argmax(lg, out=tok.view(-1))
+            toks.append(tok[rows, 0].clone())
+        torch.cuda.synchronize()
+        assert cache.num_items() == P + NT - 1
+        assert model.stats()["launches"] > 0
+    finally:
+        model.set_decode_graph(False)
+    got = torch.stack(step_logits).cpu().numpy()               # [NT, 4, V]; entry 0 = prefill's last position
+    picked = torch.stack(toks).cpu().numpy()                   # [NT, 4]
+    t = time.perf_counter()
+    oc = O.KVCache()
+    want = [O.forward(cfg, wn, prompt[rows], oc, logit_positions=[P - 1]).logits[:, 0]]
+    for i in range(NT - 1):
+        want.append(O.forward(cfg, wn, picked[i][:, None], oc).logits[:, 0])
+    want = np.stack(want)
+    print(f"[oracle] config #5 rows {rows}, {NT} cached steps: {time.perf_counter() - t:.1f} s", flush=True)
+    std = want.std()
+    d = np.abs(got - want)
+    per_step = d.max(axis=(1, 2)) / std
+    print(f"[parity] config#5 decode B=64 P=16: per-step max/std: first {per_step[0]:.4g} worst {per_step.max():.4g} "
+          f"(step {int(per_step.argmax())}) last {per_step[-1]:.4g}; mean/std {d.mean() / std:.4g}", flush=True)
+    assert per_step.max() <= MAX_REL and d.mean() / std <= MEAN_REL
+    agree = float((want.argmax(-1) == picked).mean())
+    # where they differ, the engine's pick must be a near-tie in the oracle's logits (inside the stated error)
+    gap = want.max(-1) - np.take_along_axis(want, picked[..., None], -1)[..., 0]
+    print(f"[parity] config#5 greedy token agreement {agree:.4f}; worst oracle-logit gap of a differing pick {gap.max():.4g}", flush=True)
+    assert agree >= 0.9 and gap.max() <= 2 * MAX_REL * std
+
+
+def test_config3_llama3b_s8192_trimmed_depth():
+    """BASELINE config #3 widths: Llama-3.2-3B (H=3072, 24 q heads / 8 kv heads, head_dim 128), S = 8192, B = 2 per
+    GPU as in bench.py; depth trimmed to 2 layers for the float64 oracle."""
+    cfg = O.llama_config("3b", num_hidden_layers=2)
+    w = O.synth_weights(cfg, seed=3, std=0.02)
+    wn = O.to_numpy_f32(w)
+    B, S, V = 2, 8192, cfg.vocab_size
+    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, max_positions=S)
+    del w
+    ids = np.random.default_rng(77).integers(0, V, (B, S)).astype(np.int64)
+    rows, pos = [B - 1], positions_for(S)
+    _, logits, _, hs, _ = model(ids, use_cache=False, logits_mode=LOGITS_ALL)
+    got_lg = logits[rows][:, pos].cpu().numpy()
+    got_hs = torch.stack(hs)[:, rows].cpu().numpy()
+    del logits, hs, model
+    t = time.perf_counter()
+    want = O.forward(cfg, wn, ids[rows], logit_positions=pos)
+    print(f"[oracle] config #3 row {rows}: {time.perf_counter() - t:.1f} s", flush=True)
+    agree = check_logits("config#3 3B-widths HD=128 S=8192 L=2 logits", got_lg, want.logits)
+    assert agree >= 0.9
+    check_hidden("config#3", got_hs, want.hidden_states)
+
+
+@pytest.mark.parametrize("flags", ["reference", "hf"])
+def test_config4_gemma2_2b_s4096_trimmed_depth(flags):
+    """BASELINE config #4 widths: Gemma-2-2B (H=2304, 8 q / 4 kv heads, head_dim 256, V=256000), S = 4096; depth
+    trimmed to 2 layers.  "reference": the reference's semantics (no attention soft-cap / window), B = 4 so that
+    B*S*V = 4.19e9 > 2^31 elements of logits (16.8 GB).  "hf": attention soft-cap 50, query_pre_attn_scalar scaling
+    and a 1024-token sliding window on even layers (shorter than S, so the window predicate is live at head_dim 256)."""
+    hf = flags == "hf"
+    over = dict(num_hidden_layers=2)
+    if hf:
+        over.update(sliding_window=1024, query_pre_attn_scalar=224)
+    cfg = O.gemma2_config("2b", **over)
+    w = O.synth_weights(cfg, seed=5, std=0.02, norm_jitter=0.05)
+    wn = O.to_numpy_f32(w)
+    B, S, V = (1, 4096, cfg.vocab_size) if hf else (4, 4096, cfg.vocab_size)
+    model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, max_positions=S, hf_flags=hf)
+    del w
+    ids = np.random.default_rng(55).integers(0, V, (B, S)).astype(np.int64)
+    rows, pos = [B - 1], positions_for(S)
+    _, logits, _, hs, _ = model(ids, use_cache=False, logits_mode=LOGITS_ALL)
+    assert logits.numel() == B * S * V and (hf or logits.numel() > 2 ** 31)
+    got_lg = logits[rows][:, pos].cpu().numpy()
+    got_hs = torch.stack(hs)[:, rows].cpu().numpy()
+    del logits, hs, model
+    ex = O.Extras(attn_softcap=cfg.attn_logit_softcapping, sliding_window=cfg.sliding_window,
+                  attn_scale=cfg.query_pre_attn_scalar ** -0.5, always_causal=True) if hf else None
+    t = time.perf_counter()
+    want = O.forward(cfg, wn, ids[rows], logit_positions=pos, extras=ex)
+    print(f"[oracle] config #4 ({flags}) row {rows}: {time.perf_counter() - t:.1f} s", flush=True)
+    agree = check_logits(f"config#4 gemma-2-2b-widths HD=256 V=256000 S=4096 L=2 ({flags} flags) logits", got_lg, want.logits)
+    assert agree >= 0.9
+    check_hidden(f"config#4 {flags}", got_hs, want.hidden_states)

@@ -2,9 +2,10 @@
 Python surface (which drives the C ABI), against (a) the committed golden outputs of the reference
 itself and (b) the NumPy oracle on the same seeded inputs.
 
-Stated tolerance (bf16 tensor-core operands, fp32 accumulation/residual/logits):
-    max-abs error  <= 0.15 * std(reference logits)     (measured expectation ~0.07)
-    mean-abs error <= 0.025 * std(reference logits)    (measured expectation ~0.01)
+Stated tolerance (bf16 tensor-core operands, fp32 accumulation/residual/logits), set at
+~1.5x what is measured on B200 (max/std <= 0.066, mean/std <= 0.0115 over every case below):
+    max-abs error  <= 0.10 * std(reference logits)
+    mean-abs error <= 0.018 * std(reference logits)
 BASELINE.json's literal 1e-2 max-abs is NOT reachable with bf16 operands at logit-std ~0.9 (SURVEY
 section 7, 6.3e-2 for the best pure-bf16 policy); the tests print the achieved figures.
 """
@@ -18,7 +19,7 @@ from conftest import load_golden
 from oracle import np_oracle as O
 import llm_np_cp_b200 as M
 
-MAX_REL, MEAN_REL = 0.15, 0.025
+MAX_REL, MEAN_REL = 0.10, 0.018
 
 
 def build(meta, **kw):
@@ -69,6 +70,10 @@ def test_decode_with_cache_vs_reference_golden(name):
         check_close(lg.cpu().numpy(), arr["decode_logits"][i], f"{name} step {i}")
     assert cache.num_items() == S + dec
     assert tuple(cache.key_cache[0].shape) == (arr["ids"].shape[0], cfg.num_key_value_heads, S + dec, cfg.head_dim)
+    # list-like, lazily read per layer (llama3.2_model_numpy.py:313-314 keeps plain per-layer lists)
+    assert len(cache.key_cache) == len(cache.value_cache) == cfg.num_hidden_layers
+    assert tuple(cache.value_cache[-1].shape) == tuple(cache.key_cache[0].shape)
+    assert len(list(cache.key_cache)) == cfg.num_hidden_layers and len(M.KVCache().key_cache) == 0
 
 
 def test_decode_graph_matches_plain():
@@ -159,7 +164,7 @@ def test_llama_1b_config1_vs_reference_golden_and_oracle():
     check_close(lg[:, -1, :], arr["logits_last"], "1B last-position logits")
     agree = (lg.argmax(-1) == arr["argmax"]).mean()
     print(f"[parity] 1B argmax agreement {agree:.3f}")
-    assert agree >= 0.8
+    assert agree >= 0.98
     hid = torch.stack(hs).cpu().numpy()[:, :, :, ::8]
     for i in range(hid.shape[0]):
         d = np.abs(hid[i] - arr["hidden_sub"][i])
@@ -170,6 +175,91 @@ def test_llama_1b_config1_vs_reference_golden_and_oracle():
     assert torch.equal(lg3[0], lg3[1]) and torch.equal(lg3[0], lg3[2])
     _, lg1, _, _, _ = model(arr["ids"], use_cache=False, output_hidden_states=False)
     assert torch.equal(lg3[0], lg1[0])          # same sequence alone or inside a batch: bit-identical
+
+
+def test_call_variants_vs_reference_golden():
+    """The other call forms of the reference's __call__, against outputs of the reference itself:
+    inputs_embeds, caller position_ids, a kv_cache passed with use_cache=False, and the `attentions` tuple through the
+    opt-in attention-probability path."""
+    meta, arr = load_golden("llama_tiny_call_variants")
+    cfg, w, model = build(meta)
+    model.materialize_attentions = True
+    _, logits, _, _, att = model(arr["ids"], use_cache=False)
+    check_close(logits.cpu().numpy(), arr["logits"], "variants: plain logits")
+    assert len(att) == cfg.num_hidden_layers and tuple(att[0].shape) == arr["attn_all"][0].shape
+    got = torch.stack(att).cpu().numpy()
+    d = np.abs(got - arr["attn_all"])
+    print(f"[parity] attentions (all {len(att)} layers): max_abs={d.max():.4g} (probabilities), row sums {got.sum(-1).min():.6f}..{got.sum(-1).max():.6f}")
+    assert d.max() <= 0.02 and np.abs(got.sum(-1) - 1).max() < 1e-4
+    assert (got[arr["attn_all"] == 0] == 0).all()                      # masked entries are exactly zero, like exp(-inf)
+    model.materialize_attentions = False
+    assert model(arr["ids"], use_cache=False)[4] is None
+    _, le, _, _, _ = model(None, inputs_embeds=arr["embeds"], use_cache=False)
+    check_close(le.cpu().numpy(), arr["embeds_logits"], "variants: inputs_embeds")
+    _, lp, _, _, _ = model(arr["ids"], position_ids=arr["pos_ids"], use_cache=False)
+    check_close(lp.cpu().numpy(), arr["pos_logits"], "variants: position_ids")
+    with pytest.raises(ValueError):
+        model(arr["ids"], inputs_embeds=arr["embeds"])
+    with pytest.raises(ValueError):
+        model(None)
+    cache = M.KVCache(max_tokens=32)
+    _, l1, c1, _, _ = model(arr["ids"][:, :5], use_cache=False, kv_cache=cache)
+    assert c1 is cache and cache.num_items() == meta["nocache_items_after_call1"]      # appended although use_cache=False
+    model.materialize_attentions = True
+    _, l2, _, _, a2 = model(arr["ids"][:, 5:6], use_cache=False, kv_cache=cache)
+    assert cache.num_items() == meta["nocache_items_after_call2"]
+    check_close(l1.cpu().numpy(), arr["nocache_logits1"], "variants: use_cache=False call 1")
+    check_close(l2.cpu().numpy(), arr["nocache_logits2"], "variants: use_cache=False call 2 (positions restart at 0)")
+    assert np.abs(a2[0].cpu().numpy() - arr["nocache_attn2"]).max() <= 0.02
+
+
+@pytest.mark.parametrize("tag", ["default", "swapped"])
+def test_gemma2_hf_flags_vs_transformers_golden(tag):
+    """Gemma-2 HF semantics (attention soft-cap, query_pre_attn_scalar, sliding window per layer_types) against outputs
+    of transformers' Gemma2ForCausalLM (tests/golden/hf_gemma2_tiny_flags.npz, oracle/make_golden_r2.py)."""
+    meta, arr = load_golden("hf_gemma2_tiny_flags")
+    cfg = O.gemma2_config("tiny", sliding_window=meta["sliding_window"], query_pre_attn_scalar=meta["query_pre_attn_scalar"])
+    cfg["layer_types"] = meta["layer_types"][tag]
+    w = O.synth_weights(cfg, meta["wseed"], meta["std"], meta["jitter"])
+    model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, hf_flags=True)
+    _, logits, _, hs, _ = model(arr["ids"], use_cache=False)
+    check_close(logits.cpu().numpy(), arr[f"logits_{tag}"], f"gemma2 HF flags vs transformers ({tag} layer_types)")
+    for i, h in enumerate(hs):
+        check_close(h.cpu().numpy(), arr[f"hidden_{tag}"][i], f"gemma2 HF flags hidden[{i}] ({tag})")
+    other = "swapped" if tag == "default" else "default"
+    assert np.abs(logits.cpu().numpy() - arr[f"logits_{other}"]).max() > 0.15 * arr[f"logits_{other}"].std()
+
+
+def test_decode_graph_survives_cache_recreation():
+    """Captured decode graphs are keyed on a never-reused cache id, not on the cache's heap address: destroying a cache
+    and creating another one (very likely at the same address) with the same stable id / logits buffers must not replay
+    a graph that points into the freed cache."""
+    meta, arr = load_golden("llama_tiny_decode")
+    cfg, w, model = build(meta)
+    ids = np.random.default_rng(8).integers(0, cfg.vocab_size, (2, 10))
+    tok = torch.empty((2, 1), dtype=torch.int64, device="cuda")
+    lg = torch.empty((2, cfg.vocab_size), dtype=torch.float32, device="cuda")
+
+    def run(prompt_len, graph):
+        model.set_decode_graph(graph)
+        cache = M.KVCache(max_tokens=16)
+        model(ids[:, :prompt_len], use_cache=True, kv_cache=cache, output_hidden_states=False)
+        out = []
+        for t in range(prompt_len, 10):
+            tok.copy_(torch.from_numpy(ids[:, t:t + 1]))
+            model(tok, use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=2, logits_out=lg)
+            out.append(lg.clone())
+        return torch.stack(out).cpu().numpy()
+
+    a = run(4, True)
+    b = run(6, True)               # new cache, same tok/lg pointers, different history
+    assert np.array_equal(a, run(4, False)) and np.array_equal(b, run(6, False))
+    # without a caller logits buffer every step still replays one graph (model-owned step buffers)
+    model.set_decode_graph(True)
+    cache = M.KVCache(max_tokens=16)
+    model(ids[:, :4], use_cache=True, kv_cache=cache, output_hidden_states=False)
+    outs = [model(ids[:, t:t + 1], use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=2)[1] for t in range(4, 10)]
+    assert np.array_equal(torch.stack(outs).cpu().numpy(), a)
 
 
 def test_gemma2_hf_flags_vs_oracle_extras():
