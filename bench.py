@@ -118,7 +118,7 @@ def cpu_reference_sample(cfg, sample_tokens, steps, warmup):
     return sample_tokens / dt, dt, kind
 
 
-def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, steps, warmup, sample_clocks=True):
+def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, steps, warmup, sample_clocks=True, tp=1):
     """BASELINE.json config #5: autoregressive decode with the KV cache (the loop of generate(),
     llama3.2_model_numpy.py:881-909): B sequences per GPU (replicas only across GPUs), greedy feedback on the device, every
     one-token step replayed as one CUDA graph.  One rollout = `NT` one-token forwards for the batch; the prompt prefill is
@@ -128,9 +128,10 @@ def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, step
     from llm_np_cp_b200.model import LOGITS_LAST
     from llm_np_cp_b200 import dp
     V = cfg.vocab_size
-    rng = np.random.default_rng(99 + rank)
+    rng = np.random.default_rng(99 + (rank if tp <= 1 else 0))     # tensor parallel: every rank feeds the same batch
     prompt = torch.from_numpy(rng.integers(0, V, (B, P)).astype(np.int64)).to(dev)
     cache = M.KVCache(max_batch=B, max_tokens=P + NT)
+    replicas = world if tp <= 1 else 1
     model.set_decode_graph(not os.environ.get("B2_NO_GRAPH"))
     tok = torch.empty((B, 1), dtype=torch.int64, device=dev)
     tok_host = torch.empty((B, 1), dtype=torch.int64).pin_memory()
@@ -172,13 +173,14 @@ def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, step
         ms += rollout(False)[0]
     barrier()
     clocks = sampler.stop() if (rank == 0 and sampler) else None
-    launches = model.stats()["launches"]
+    stt = model.stats()
+    launches = stt["launches"]
     e2e_ms = 0.0
     for _ in range(steps):
         e2e_ms += rollout(True)[1]
     model.set_decode_graph(False)
     ms, e2e_ms = dp.max_over_ranks([ms, e2e_ms], device=dev)
-    toks = B * NT * world * steps
+    toks = B * NT * replicas * steps
     if rank != 0:
         return None
     from llm_np_cp_b200 import shapes
@@ -186,13 +188,24 @@ def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, step
     kv = cfg.num_key_value_heads * cfg.head_dim
     t_avg = P + NT / 2.0
     bytes_step = 2.0 * shapes.matmul_params(cfg) + B * t_avg * L * 2 * kv * 2   # bf16 weights once + KV read
+    if tp > 1:                                                                   # per GPU: 1/tp of everything but the embedding gather
+        bytes_step /= tp
     step_s = ms / 1e3 / (steps * NT)
     gbs = bytes_step / step_s / 1e9
+    out_tp = None
+    if tp > 1:
+        H = cfg.hidden_size
+        out_tp = {"world": tp, "nccl_calls_per_token_step": stt["comm_calls"] / (steps * NT),
+                  "payload_bytes_per_token_step": stt["comm_bytes"] / (steps * NT),
+                  "algorithmic_nvlink_bytes_per_allreduce": 2.0 * B * H * 4 * (tp - 1) / tp,
+                  "note": "2 all-reduces of [B,H] fp32 partial sums per layer (after o_proj and down_proj) + 1 all-gather of logits"}
     return {
         "metric": "decode_tokens_per_sec", "value": toks / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-        "config": {"batch_per_gpu": B, "prompt": P, "new_tokens": NT,
-                   "parallelism": f"replicas x{world} (no collective)", "sampling": "greedy argmax on device (b2_argmax)",
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak" if tp <= 1 else "strong",
+        "tp": out_tp,
+        "config": {"batch_per_gpu": B if tp <= 1 else None, "batch": B * replicas, "prompt": P, "new_tokens": NT,
+                   "parallelism": (f"replicas x{world} (no collective)" if tp <= 1 else f"tp{tp} (heads / FFN columns / vocabulary split, NCCL all-reduce over NVLink)"),
+                   "sampling": "greedy argmax on device (b2_argmax)",
                    "cuda_graph": not os.environ.get("B2_NO_GRAPH"),
                    "l2": "all weights (2.47 GB for 1B) streamed every token step >> 126 MB L2; no flush needed"},
         "ms_per_token_step": step_s * 1e3,
@@ -207,7 +220,7 @@ def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, step
 
 def bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload):
     """`--workload decode`: the decode rollout as the headline line."""
-    line = measure_decode(cfg, model, dev, dist, rank, world, local, pk, a.batch, a.prompt, a.new_tokens, a.steps, a.warmup)
+    line = measure_decode(cfg, model, dev, dist, rank, world, local, pk, a.batch, a.prompt, a.new_tokens, a.steps, a.warmup, tp=a.tp)
     if rank == 0:
         line["config"] = dict({"workload": workload}, **line["config"])
         line.update({"vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
@@ -239,6 +252,7 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=128, help="decode: generated tokens per sequence")
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (default 8 prefill / 64 decode)")
     ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel degree (= --gpus): one batch split by heads / FFN columns over the GPUs")
     ap.add_argument("--cpu-sample-tokens", type=int, default=int(os.environ.get("B2_CPU_SAMPLE_TOKENS", 16)))
     ap.add_argument("--cpu-long-sample", type=int, default=int(os.environ.get("B2_CPU_LONG_SAMPLE", 128)),
                     help="--impl reference: one extra forward at this many tokens (0 = skip)")
@@ -303,14 +317,18 @@ def main():
 
     B, S, V = a.batch, a.seq, cfg.vocab_size
     w = shapes.synth_checkpoint(cfg, seed=0, device=dev)
+    tp = a.tp if a.tp > 1 else 1
+    if tp > 1 and tp != world:
+        raise SystemExit(f"--tp {tp} needs exactly {tp} ranks (torchrun --nproc-per-node {tp}), got {world}")
+    tpkw = dict(tensor_parallel=True) if tp > 1 else {}
     if cfg.family == "gemma2":
-        model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16), hf_flags=a.hf_flags)
+        model = M.Gemma2ForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16), hf_flags=a.hf_flags, **tpkw)
     else:
-        model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16))
+        model = M.LlamaForCausalLM(M.AttributeDict(cfg), w, device=local, max_positions=max(S, a.prompt + a.new_tokens, 16), **tpkw)
     if a.workload == "decode":
         del w
         return bench_decode(a, cfg, model, dev, dist, rank, world, local, pk, workload)
-    rng = np.random.default_rng(1234 + rank)
+    rng = np.random.default_rng(1234 + (rank if tp <= 1 else 0))    # tensor parallel: every rank feeds the same batch
     ids_host = torch.from_numpy(rng.integers(0, V, (B, S)).astype(np.int64)).pin_memory()
     ids_dev = ids_host.to(dev)
     logits = None
@@ -372,13 +390,13 @@ def main():
     if dist is not None:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tm[0]), float(tm[1])
-    tokens = B * S * world * a.steps
+    tokens = B * S * (world if tp <= 1 else 1) * a.steps
     value = tokens / (ms / 1e3)
     e2e = tokens / (e2e_ms / 1e3)
 
     # ---- decode: BASELINE's metric ends "...; decode tok/s" -- a short config-#5 rollout rides along in the same line ----
     decode = None
-    if not a.no_decode and cfg.family == "llama":
+    if not a.no_decode and cfg.family == "llama" and tp <= 1:
         decode = measure_decode(cfg, model, dev, dist, rank, world, local, pk, 64, 16, 128, steps=3, warmup=1, sample_clocks=False)
 
     # ---- parity mode: what BASELINE's literal "1e-2 max-abs" costs.  Same kernels, every bf16 activation carried as hi + lo
@@ -450,6 +468,18 @@ def main():
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
         }
+        if tp > 1:
+            H = cfg.hidden_size
+            line["scaling"] = "strong"
+            line["config"]["parallelism"] = f"tp{tp} (heads / FFN columns / vocabulary split over {tp} GPUs, NCCL all-reduce over NVLink)"
+            line["config"]["global_batch"] = B
+            line["model_tflops_per_gpu"] = value * f_tok / 1e12 / tp
+            line["model_frac_of_peak"] = value * f_tok / 1e12 / tp / peak
+            line["tp"] = {"world": tp, "nccl_calls_per_step": st["comm_calls"] / a.steps, "payload_bytes_per_step": st["comm_bytes"] / a.steps,
+                          "comm_ms_per_step": st["comm_ms"] / nt, "comm_share_of_step": st["comm_ms"] / nt / step_ms,
+                          "algorithmic_nvlink_bytes_per_allreduce": 2.0 * B * S * H * 4 * (tp - 1) / tp,
+                          "allreduce_payload_bytes": B * S * H * 4,
+                          "note": "2 all-reduces of the [M,H] fp32 partial sums per layer (after o_proj and down_proj) + the all-gather of the logits"}
         if decode is not None:
             line["decode"] = decode
         if precise is not None:

@@ -58,6 +58,12 @@ typedef struct b2_config {
   float rope_low_freq_factor;           /* Llama-3.2: 1 */
   float rope_high_freq_factor;          /* Llama-3.2: 4 */
   int32_t rope_original_max_positions;  /* Llama-3.2: 8192 */
+  /* Optional tensor parallelism for single long sequences / decode (the reference has no parallelism at all; BASELINE.json
+   * north_star): this engine is rank tp_rank of tp_world engines, one per GPU.  Attention heads, FFN columns and
+   * vocabulary rows are split evenly; o_proj / down_proj produce partial sums that are summed with ncclAllReduce over
+   * NVLink, lm_head logits are all-gathered.  tp_world <= 1 = off.  b2_load_weight still takes the FULL tensors (each
+   * engine keeps its slice); b2_tp_init must follow b2_engine_create on every rank. */
+  int32_t tp_rank, tp_world;
 } b2_config;
 
 typedef struct b2_engine b2_engine;
@@ -119,6 +125,11 @@ typedef struct b2_forward_args {
   void* stream;
 } b2_forward_args;
 int b2_forward_ex(b2_engine* e, b2_cache* cache, const b2_forward_args* args);
+/* Tensor-parallel communicator.  Rank 0 calls b2_tp_unique_id (ncclGetUniqueId), the caller ships the B2_NCCL_ID_BYTES
+ * bytes to the other ranks (e.g. torch.distributed broadcast), every rank then calls b2_tp_init (ncclCommInitRank). */
+#define B2_NCCL_ID_BYTES 128
+int b2_tp_unique_id(void* id_out);
+int b2_tp_init(b2_engine* e, const void* id);
 /* HF layer_types: is_sliding[i] != 0 => layer i applies cfg.sliding_window (default without this call: even layers,
  * transformers' Gemma-2 default pattern).  No effect while cfg.sliding_window == 0 (the reference never slides). */
 int b2_set_layer_types(b2_engine* e, const int32_t* is_sliding, int n_layers);
@@ -148,6 +159,9 @@ typedef struct b2_stats {
   double attn_flops;
   int64_t attn_launches;
   int64_t timed_forwards;  /* forwards whose launches carried events (see b2_set_timing) */
+  int64_t comm_calls;      /* tensor parallelism: NCCL collectives enqueued since the last reset */
+  double comm_bytes;       /* payload bytes of those collectives on this rank */
+  double comm_ms;          /* their device time, only while timing is on */
 } b2_stats;
 /* on = 1: record CUDA events around every GEMM / attention launch; on = k > 1: only on every k-th forward (the other
  * forwards take the plain launch path, so a timed region mostly runs exactly what an untimed one runs); 0 = off */
@@ -163,6 +177,11 @@ int b2_op_add_rmsnorm(float* x_dev, const float* y_dev, const float* g_dev, int 
  * 4 GLU on a gate/up-interleaved W (out bf16 [M,N/2]).  bn: N-tile (32/64/128/256), split_k >= 1 (epi 2 only). */
 int b2_op_gemm(const void* a_bf16_dev, const void* w_bf16_dev, void* out_dev, int M, int N, int K, int epi,
                int bn, int split_k, float softcap, int act, void* stream);
+/* few-row (M <= 64) cluster split-K GEMM of the decode step with the residual-add + half-RMSNorm epilogue:
+ * x[M,N] fp32 += a[M,K] . w[N,K]^T;  a_out[M,N] bf16 = x * gamma;  ss[M,N/32] = sums of x^2 per 32-column block.
+ * cluster = CTAs per 64-column output tile, reduced through distributed shared memory (0 = one wave of the device). */
+int b2_op_gemm_sk(const void* a_bf16_dev, const void* w_bf16_dev, float* x_dev, void* a_out_bf16_dev, const float* gamma_dev,
+                  float* ss_dev, int M, int N, int K, int cluster, void* stream);
 /* fused QKV projection + RoPE + KV append: a [B*S,H] bf16, w [(NH+2NKV)*HD, H] bf16 ->
  * q [B*S, NH*HD] bf16, k/v caches [B][NKV][Tmax][HD] bf16 written at positions t0..t0+S-1 */
 int b2_op_qkv_rope(const void* a_dev, const void* w_dev, void* q_dev, void* k_cache_dev, void* v_cache_dev, int B,

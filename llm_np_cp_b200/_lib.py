@@ -19,13 +19,15 @@ class B2Config(C.Structure):
                 ("gemma", C.c_int32), ("final_logit_softcap", C.c_float), ("attn_logit_softcap", C.c_float),
                 ("sliding_window", C.c_int32), ("attn_scale", C.c_float), ("always_causal", C.c_int32),
                 ("precise", C.c_int32), ("rope_factor", C.c_float), ("rope_low_freq_factor", C.c_float),
-                ("rope_high_freq_factor", C.c_float), ("rope_original_max_positions", C.c_int32)]
+                ("rope_high_freq_factor", C.c_float), ("rope_original_max_positions", C.c_int32),
+                ("tp_rank", C.c_int32), ("tp_world", C.c_int32)]
 
 
 class B2Stats(C.Structure):
     _fields_ = [("launches", C.c_int64), ("gemm_launches", C.c_int64), ("gemm_ms", C.c_double),
                 ("gemm_flops", C.c_double), ("attn_ms", C.c_double), ("attn_flops", C.c_double),
-                ("attn_launches", C.c_int64), ("timed_forwards", C.c_int64)]
+                ("attn_launches", C.c_int64), ("timed_forwards", C.c_int64), ("comm_calls", C.c_int64),
+                ("comm_bytes", C.c_double), ("comm_ms", C.c_double)]
 
 
 class B2ForwardArgs(C.Structure):
@@ -51,6 +53,8 @@ SYMBOLS = [
     ("b2_forward", _I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     ("b2_forward_ex", _I, [_P, _P, C.POINTER(B2ForwardArgs)]),
     ("b2_set_layer_types", _I, [_P, C.POINTER(C.c_int32), _I]),
+    ("b2_tp_unique_id", _I, [_P]),
+    ("b2_tp_init", _I, [_P, _P]),
     ("b2_forward_host", _I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     ("b2_set_decode_graph", _I, [_P, _I]),
     ("b2_sample_min_p", _I, [_P, _P, _I, _I, _F, _P, _P, _P, _P]),
@@ -61,6 +65,7 @@ SYMBOLS = [
     ("b2_op_rmsnorm", _I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     ("b2_op_add_rmsnorm", _I, [_P, _P, _P, _I, _I, _F, _P]),
     ("b2_op_gemm", _I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
+    ("b2_op_gemm_sk", _I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     ("b2_op_qkv_rope", _I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     ("b2_op_attention", _I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P]),
     ("b2_interleave_gate_up", _I, [_P, _P, _P, _I, _I]),

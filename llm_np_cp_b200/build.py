@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200fwd.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "gemm_tcgen05.cuh", "gemm2_tcgen05.cuh", "attention_tcgen05.cuh", "elementwise.cuh",
+HEADERS = ["common.cuh", "gemm_tcgen05.cuh", "gemm2_tcgen05.cuh", "gemm_sk_tcgen05.cuh", "attention_tcgen05.cuh", "elementwise.cuh",
            os.path.join("..", "..", "include", "b200fwd.h")]
 
 

@@ -1103,10 +1103,15 @@ attn_decode_split_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
       acc = fmaf(wgt, s_merge[(w * DEC_MAX_NREP + j) * PW + d], acc);
       ls = fmaf(wgt, s_merge[(w * DEC_MAX_NREP + j) * PW + HD + 1], ls);
     }
+    if (nsplit == 1) {   // short cache, one slice per (batch, kv head): this CTA holds the whole row -- no partials, no counter
+      out[static_cast<size_t>(b) * ldo + (kvh * nrep + j) * HD + d] = __float2bfloat16_rn(ls > 0.f ? acc / ls : 0.f);
+      continue;
+    }
     float* pr = part + ((pbase + static_cast<size_t>(j) * nsplit) + sp) * PW;
     pr[d] = acc;
     if (d == 0) pr[HD] = m_all, pr[HD + 1] = ls;
   }
+  if (nsplit == 1) return;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {

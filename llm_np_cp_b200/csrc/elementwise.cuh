@@ -100,15 +100,58 @@ attn_probs_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
   for (int t = lane; t < T; t += 32) o[t] *= inv;
 }
 
+// Decode step with the RMSNorm split across the GEMMs (gemm_sk_tcgen05.cuh): x = table[id] * scale, a' = bf16(x * gamma)
+// (the first GEMM's A operand), ss[row][0] = sum x^2 and ss[row][1..ss_n) = 0.  One CTA per row.
+__global__ void __launch_bounds__(256)
+embed_norm_row_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ table, float* __restrict__ x,
+                      __nv_bfloat16* __restrict__ a_out, const float* __restrict__ gamma, float* __restrict__ ss, int ss_n, int H,
+                      int V, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  long long id = ids[row];
+  if (id < 0) id = 0;
+  if (id >= V) id = V - 1;
+  const uint2* src = reinterpret_cast<const uint2*>(table + static_cast<size_t>(id) * H);
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float sq = 0.f;
+  for (int i = tid; i < H / 4; i += 256) {
+    const uint2 u = __ldg(src + i);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    const float4 v = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+    xr[i] = v;
+    sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    const float4 gg = __ldg(g4 + i);
+    *reinterpret_cast<uint2*>(a_out + static_cast<size_t>(row) * H + i * 4) =
+        make_uint2(pack_bf16(v.x * gg.x, v.y * gg.y), pack_bf16(v.z * gg.z, v.w * gg.w));
+  }
+  sq = warp_sum(sq);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  __syncthreads();
+  float* srow = ss + static_cast<size_t>(row) * ss_n;
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    srow[0] = t;
+  }
+  for (int i = 1 + tid; i < ss_n; i += 256) srow[i] = 0.f;
+}
+
 constexpr int NORM_MAXV = 24;  // float4 per lane: supports H <= 3072
 
 // out = x * 1/sqrt(mean(x^2)+eps) * g   (LlamaRMSNorm_np, llama3.2_model_numpy.py:256-278; g already holds
 // (1 + gamma) for Gemma-2, gemma2_model.py:334).  One warp per row; the row stays in registers between the
 // reduction and the scaling pass.  Writes bf16 (the next GEMM's A operand; optional "lo" plane at
 // +lo_off columns for the precise mode) and/or fp32 (hidden-state capture / final norm).
+// `add` (optional): x[row] += add[row] first, written back -- the all-reduced partial sums of a row-parallel o_proj /
+// down_proj under tensor parallelism (the residual add of llama3.2_model_numpy.py:569, :578).
 __global__ void __launch_bounds__(256)
-rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16,
-               int ld_out, int lo_off, float* __restrict__ out_f32, int M, int H, float eps) {
+rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ g,
+               __nv_bfloat16* __restrict__ out_bf16, int ld_out, int lo_off, float* __restrict__ out_f32, int M, int H, float eps) {
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,13 +160,19 @@ rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bf
   const int row = M - 1 - (blockIdx.x * 8 + warp);
   if (row < 0) return;
   const int nv = H >> 7;  // float4 per lane
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * H);
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H);
+  const float4* ar = add ? reinterpret_cast<const float4*>(add + static_cast<size_t>(row) * H) : nullptr;
   float4 v[NORM_MAXV];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NORM_MAXV; ++i) {
     if (i < nv) {
       v[i] = xr[i * 32 + lane];
+      if (ar) {
+        const float4 a4 = ar[i * 32 + lane];
+        v[i].x += a4.x; v[i].y += a4.y; v[i].z += a4.z; v[i].w += a4.w;
+        xr[i * 32 + lane] = v[i];
+      }
       ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     }
   }
@@ -432,4 +481,21 @@ min_p_sample_kernel(const float* __restrict__ logits, int ld, int V, float p_bas
   }
 }
 
+}  // namespace b2
+
+namespace b2 {
+// vocabulary-parallel lm_head (tensor parallelism): ncclAllGather leaves [world][rows][V_local]; the caller's logits are
+// [rows][world * V_local].  One float4 per thread, coalesced on both sides.
+__global__ void __launch_bounds__(256)
+tp_unshard_logits_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int v_local, int world) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t vl4 = static_cast<size_t>(v_local) / 4, n4 = static_cast<size_t>(rows) * world * vl4;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t c = i % vl4, r = (i / vl4) % rows, w = i / (vl4 * rows);
+    d4[(r * world + w) * vl4 + c] = s4[i];
+  }
+}
 }  // namespace b2

@@ -13,11 +13,15 @@
 #include <tuple>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the entry points are resolved with dlopen, libb200fwd.so has no link-time NCCL dependency
+
 #include "../../include/b200fwd.h"
 #include "attention_tcgen05.cuh"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm2_tcgen05.cuh"
+#include "gemm_sk_tcgen05.cuh"
 
 using namespace b2;
 typedef __nv_bfloat16 bf16;
@@ -79,6 +83,53 @@ static int require_gpu(int device) {
   if (device < 64) ok.fetch_or(1ull << device, std::memory_order_release);
   return B2_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// NCCL (optional tensor-parallel path): resolved at run time.  The process usually already has a libnccl.so.2 loaded
+// (torch's); RTLD_NOLOAD picks that one up, otherwise the system library is opened.
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static const NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::atomic<int> state{0};   // 0 = not tried, 1 = ok, -1 = unavailable
+  static std::atomic_flag busy = ATOMIC_FLAG_INIT;
+  if (state.load(std::memory_order_acquire) == 1) return &api;
+  while (busy.test_and_set(std::memory_order_acquire)) {}
+  if (state.load() == 0) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    bool ok = h != nullptr;
+    if (ok) {
+      api.h = h;
+#define B2_SYM(field, name) ok = ok && ((*reinterpret_cast<void**>(&api.field) = dlsym(h, name)) != nullptr)
+      B2_SYM(GetUniqueId, "ncclGetUniqueId");
+      B2_SYM(CommInitRank, "ncclCommInitRank");
+      B2_SYM(CommDestroy, "ncclCommDestroy");
+      B2_SYM(AllReduce, "ncclAllReduce");
+      B2_SYM(AllGather, "ncclAllGather");
+      B2_SYM(GetErrorString, "ncclGetErrorString");
+#undef B2_SYM
+    }
+    state.store(ok ? 1 : -1, std::memory_order_release);
+  }
+  busy.clear(std::memory_order_release);
+  return state.load() == 1 ? &api : nullptr;
+}
+#define CKN(call)                                                                                         \
+  do {                                                                                                    \
+    ncclResult_t _r = (call);                                                                             \
+    if (_r != ncclSuccess)                                                                                \
+      return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(_r), __FILE__, __LINE__); \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------
 // TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
@@ -225,6 +276,58 @@ static int launch_gemm2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
   if (epi == EPI_QKV_ROPE) return launch_gemm2_t<EPI_QKV_ROPE>(ta, tb, tc, p, st);
   if (epi == EPI_GLU) return launch_gemm2_t<EPI_GLU>(ta, tb, tc, p, st);
   return fail(B2_ERR_ARG, "bad epilogue %d", epi);
+}
+
+// few-row cluster split-K GEMM (gemm_sk_tcgen05.cuh): grid = tiles x CK, cluster = the CK CTAs that share an output tile
+template <int EPI>
+static int launch_gemm_sk_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_sk_kernel<EPI>;
+  static std::atomic<uint64_t> attr{0};
+  CKR(smem_attr_once(kern, GemmSkCfg::SMEM_BYTES, attr));
+  const int tiles = ((p.N + SK_BN - 1) / SK_BN);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(tiles * p.split_k);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GemmSkCfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (p.split_k > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = p.split_k;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  CK(cudaLaunchKernelEx(&cfg, kern, ta, tb, ta, p));
+  return B2_OK;
+}
+static int launch_gemm_sk(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if (p.M > SK_MAX_ROWS || p.M <= 0) return fail(B2_ERR_ARG, "cluster split-K GEMM handles 1..%d rows (got %d)", SK_MAX_ROWS, p.M);
+  if (p.K % GEMM_BK || p.N % SK_BN) return fail(B2_ERR_ARG, "cluster split-K GEMM needs K %% 64 == 0 and N %% 64 == 0 (K=%d N=%d)", p.K, p.N);
+  if (p.split_k < 1 || p.split_k > SK_MAX_CLUSTER || (p.K / GEMM_BK) % p.split_k)
+    return fail(B2_ERR_ARG, "cluster size %d must be 1..%d and divide K/64 = %d", p.split_k, SK_MAX_CLUSTER, p.K / GEMM_BK);
+  if (epi == EPI_QKV_ROPE) {
+    if (p.head_dim != SK_BN) return fail(B2_ERR_ARG, "cluster split-K QKV epilogue needs head_dim == %d", SK_BN);
+    return launch_gemm_sk_t<EPI_QKV_ROPE>(ta, tb, p, st);
+  }
+  if (epi == EPI_RESID_NORM) return launch_gemm_sk_t<EPI_RESID_NORM>(ta, tb, p, st);
+  return fail(B2_ERR_ARG, "no cluster split-K instantiation for epilogue %d", epi);
+}
+// cluster size for a few-row GEMM with `tiles` output tiles and `kb` k-blocks: as many CTAs as fit one wave
+static int pick_cluster(int tiles, int kb, int n_sms) {
+  int best = 1;
+  for (int ck = 2; ck <= SK_MAX_CLUSTER; ++ck)
+    if (kb % ck == 0 && kb / ck >= 2 && tiles * ck <= n_sms) best = ck;
+  return best;
 }
 
 static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
@@ -474,7 +577,17 @@ struct b2_engine {
   int device;
   cudaStream_t stream = nullptr;
   bool finalized = false;
-  int q_cols, kv_cols, qkv_n;
+  // Shapes of THIS rank's shard (== the model's when tp_world == 1): heads, FFN columns and vocabulary rows are split
+  // evenly over the tensor-parallel ranks; hidden_size is never split.
+  int tp_rank = 0, tp_world = 1;
+  int nh = 0, nkv = 0, I = 0, V = 0;    // local q heads, kv heads, intermediate columns, vocabulary rows
+  int q_cols, kv_cols, qkv_n;           // local widths: nh*HD, nkv*HD, (nh + 2 nkv)*HD
+  ncclComm_t comm = nullptr;
+  float* tp_lg = nullptr;               // vocab-parallel lm_head: local [rows, V_local] logits, gathered [world][rows][V_local]
+  float* tp_gather = nullptr;
+  size_t tp_lg_elems = 0;
+  int64_t comm_calls = 0;
+  double comm_bytes = 0;
   bf16* embed = nullptr;
   float* g_final = nullptr;
   bool embed_loaded = false, final_loaded = false;
@@ -484,6 +597,7 @@ struct b2_engine {
   int ws_tokens = 0, ws_batch = 0;
   float *x = nullptr, *y = nullptr, *xl = nullptr, *part = nullptr;   // part: [MAX_SPLIT][128][H] split-K partials (skinny GEMMs)
   bf16 *xn = nullptr, *q = nullptr, *att = nullptr, *hb = nullptr, *xnl = nullptr;
+  float* ss = nullptr;                   // [64][H/32] per-row partial sums of squares (decode step with the norm split across GEMMs)
   int64_t* ids_ws = nullptr;
   float* logits_ws = nullptr;
   size_t logits_ws_elems = 0;
@@ -578,16 +692,31 @@ static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* 
   return r;
 }
 
+// few-row cluster split-K GEMM through the engine (decode step)
+static int eng_gemm_sk(b2_engine* e, cudaStream_t st, int epi, const bf16* a, int lda, const bf16* w, GemmParams p) {
+  CUtensorMap ta, tb;
+  p.a_box_rows = p.M <= 32 ? 32 : 64;
+  p.split_k = pick_cluster(p.N / SK_BN, p.K / GEMM_BK, e->n_sms);
+  CKR(get_tmap(e, a, e->ws_tokens > p.M ? e->ws_tokens : p.M, p.K, lda, p.a_box_rows, &ta));
+  CKR(get_tmap(e, w, p.N, p.K, p.K, SK_BN, &tb));
+  time_begin(e, st, 2.0 * p.M * static_cast<double>(p.N) * p.K, 0);
+  int r = launch_gemm_sk(epi, ta, tb, p, st);
+  time_end(e, st);
+  e->st.launches++;
+  e->st.gemm_launches++;
+  return r;
+}
+
 extern "C" void b2_engine_destroy(b2_engine* e);
 // device allocations of b2_engine_create (separate so that a failure half-way can be unwound by b2_engine_destroy)
 static int engine_alloc(b2_engine* e) {
   const b2_config& c = e->cfg;
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  e->q_cols = c.num_attention_heads * c.head_dim;
-  e->kv_cols = c.num_key_value_heads * c.head_dim;
+  e->q_cols = e->nh * c.head_dim;
+  e->kv_cols = e->nkv * c.head_dim;
   e->qkv_n = e->q_cols + 2 * e->kv_cols;
   if (e->qkv_n % 32) return fail(B2_ERR_ARG, "fused QKV width %d must be a multiple of 32", e->qkv_n);
-  const size_t H = c.hidden_size, I = c.intermediate_size;
+  const size_t H = c.hidden_size, I = e->I;
   CK(cudaMalloc(&e->embed, static_cast<size_t>(c.vocab_size) * H * 2));
   CK(cudaMalloc(&e->g_final, H * 4));
   e->layers.resize(c.num_hidden_layers);
@@ -632,10 +761,26 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
   if (c.vocab_size % 32) return fail(B2_ERR_ARG, "vocab_size %d must be a multiple of 32", c.vocab_size);
   if (c.max_positions <= 0) return fail(B2_ERR_ARG, "max_positions must be positive");
   if (c.precise && c.head_dim == 256) return fail(B2_ERR_ARG, "precise (hi/lo split) mode supports head_dim 64 and 128 only");
+  const int tpw = c.tp_world > 1 ? c.tp_world : 1;
+  if (tpw > 1) {
+    if (c.tp_rank < 0 || c.tp_rank >= tpw) return fail(B2_ERR_ARG, "tp_rank %d outside [0, %d)", c.tp_rank, tpw);
+    if (c.precise) return fail(B2_ERR_ARG, "tensor parallelism is not available in precise mode");
+    if (c.num_attention_heads % tpw || c.num_key_value_heads % tpw)
+      return fail(B2_ERR_ARG, "tp_world %d must divide the %d query heads and the %d key/value heads", tpw, c.num_attention_heads,
+                  c.num_key_value_heads);
+    if (c.intermediate_size % (64 * tpw)) return fail(B2_ERR_ARG, "tp_world %d: intermediate_size %d must be a multiple of %d", tpw, c.intermediate_size, 64 * tpw);
+    if (c.vocab_size % (32 * tpw)) return fail(B2_ERR_ARG, "tp_world %d: vocab_size %d must be a multiple of %d", tpw, c.vocab_size, 32 * tpw);
+  }
   CK(cudaSetDevice(device));
   b2_engine* e = new b2_engine();
   e->cfg = c;
   e->device = device;
+  e->tp_world = tpw;
+  e->tp_rank = tpw > 1 ? c.tp_rank : 0;
+  e->nh = c.num_attention_heads / tpw;
+  e->nkv = c.num_key_value_heads / tpw;
+  e->I = c.intermediate_size / tpw;
+  e->V = c.vocab_size / tpw;
   e->n_sms = num_sms();
   e->sliding.assign(c.num_hidden_layers, 0);
   for (int i = 0; i < c.num_hidden_layers; i += 2) e->sliding[i] = 1;   // HF Gemma-2 default layer_types: even layers slide
@@ -650,7 +795,8 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
 
 static void free_ws(b2_engine* e) {
   cudaFree(e->x); cudaFree(e->y); cudaFree(e->xl); cudaFree(e->part); cudaFree(e->xn); cudaFree(e->q); cudaFree(e->att);
-  cudaFree(e->hb); cudaFree(e->xnl); cudaFree(e->ids_ws);
+  cudaFree(e->hb); cudaFree(e->xnl); cudaFree(e->ids_ws); cudaFree(e->ss);
+  e->ss = nullptr;
   e->x = e->y = e->xl = e->part = nullptr;
   e->xn = e->q = e->att = e->hb = e->xnl = nullptr;
   e->ids_ws = nullptr;
@@ -688,6 +834,8 @@ extern "C" void b2_engine_destroy(b2_engine* e) {
   if (e->scratch) b2_cache_destroy(e->scratch);
   for (b2_cache* c : e->caches) c->e = nullptr;   // caches that outlive the engine (GC order) still free their own memory
   cudaFree(e->logits_ws);
+  cudaFree(e->tp_lg); cudaFree(e->tp_gather);
+  if (e->comm && nccl_api()) nccl_api()->CommDestroy(e->comm);
   cudaFree(e->embed); cudaFree(e->g_final); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
   for (auto& L : e->layers) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd);
@@ -772,34 +920,49 @@ extern "C" int b2_load_weight(b2_engine* e, const char* name, const void* host, 
     L.loaded |= bit;
     return B2_OK;
   };
-  auto mat = [&](bf16* dst, int64_t r, int64_t cc, unsigned bit) -> int {
-    CKR(want(r, cc));
-    to_bf16_host(host, static_cast<size_t>(r) * cc, dtype, hb);
+  // The caller always passes the FULL HF tensor (the reference's load_weights(name) seam); under tensor parallelism this
+  // rank keeps its slice: `rows` tensors (q/k/v/gate/up: output features) a contiguous row block, `cols` tensors
+  // (o_proj/down_proj: input features) a column block.
+  const int64_t tw = e->tp_world, tr = e->tp_rank;
+  const size_t esz = dtype == B2_DTYPE_F32 ? 4 : 2;
+  auto rows = [&](bf16* dst, int64_t r_full, int64_t cc, unsigned bit) -> int {   // dst gets rows [tr*r_full/tw, +r_full/tw)
+    CKR(want(r_full, cc));
+    const int64_t r = r_full / tw;
+    to_bf16_host(static_cast<const uint8_t*>(host) + static_cast<size_t>(tr) * r * cc * esz, static_cast<size_t>(r) * cc, dtype, hb);
     CK(cudaMemcpy(dst, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+    L.loaded |= bit;
+    return B2_OK;
+  };
+  auto cols = [&](bf16* dst, int64_t r, int64_t c_full, unsigned bit) -> int {   // dst [r, c_full/tw] = columns [tr*c_full/tw, ...)
+    CKR(want(r, c_full));
+    const int64_t cc = c_full / tw;
+    to_bf16_host(host, static_cast<size_t>(r) * c_full, dtype, hb);
+    CK(cudaMemcpy2D(dst, cc * 2, hb.data() + tr * cc, c_full * 2, cc * 2, r, cudaMemcpyHostToDevice));
     L.loaded |= bit;
     return B2_OK;
   };
   auto glu = [&](int which, unsigned bit) -> int {  // 32-row groups: [gate g | up g]
     CKR(want(I, H));
-    to_bf16_host(host, static_cast<size_t>(I) * H, dtype, hb);
+    const int64_t Il = e->I;
+    to_bf16_host(static_cast<const uint8_t*>(host) + static_cast<size_t>(tr) * Il * H * esz, static_cast<size_t>(Il) * H, dtype, hb);
     const size_t grp = 32 * H * 2;
-    CK(cudaMemcpy2D(reinterpret_cast<uint8_t*>(L.wgu) + which * grp, 2 * grp, hb.data(), grp, grp, I / 32,
+    CK(cudaMemcpy2D(reinterpret_cast<uint8_t*>(L.wgu) + which * grp, 2 * grp, hb.data(), grp, grp, Il / 32,
                     cudaMemcpyHostToDevice));
     L.loaded |= bit;
     return B2_OK;
   };
+  const int64_t qg = static_cast<int64_t>(c.num_attention_heads) * c.head_dim, kvg = static_cast<int64_t>(c.num_key_value_heads) * c.head_dim;
   if (t == "input_layernorm.weight") return norm(L.g_in, T_IN);
   if (t == "post_attention_layernorm.weight") return norm(L.g_post_attn, T_POST);
   if (t == "pre_feedforward_layernorm.weight" && c.gemma) return norm(L.g_pre_ffn, T_PRE_FFN);
   if (t == "post_feedforward_layernorm.weight" && c.gemma) return norm(L.g_post_ffn, T_POST_FFN);
-  if (t == "self_attn.q_proj.weight") return mat(L.wqkv, e->q_cols, H, T_Q);
-  if (t == "self_attn.k_proj.weight") return mat(L.wqkv + static_cast<size_t>(e->q_cols) * H, e->kv_cols, H, T_K);
-  if (t == "self_attn.v_proj.weight")
-    return mat(L.wqkv + static_cast<size_t>(e->q_cols + e->kv_cols) * H, e->kv_cols, H, T_V);
-  if (t == "self_attn.o_proj.weight") return mat(L.wo, H, e->q_cols, T_O);
+  if (t == "self_attn.q_proj.weight") return rows(L.wqkv, qg, H, T_Q);
+  if (t == "self_attn.k_proj.weight") return rows(L.wqkv + static_cast<size_t>(e->q_cols) * H, kvg, H, T_K);
+  if (t == "self_attn.v_proj.weight") return rows(L.wqkv + static_cast<size_t>(e->q_cols + e->kv_cols) * H, kvg, H, T_V);
+  if (t == "self_attn.o_proj.weight") return cols(L.wo, H, qg, T_O);
   if (t == "mlp.gate_proj.weight") return glu(0, T_GATE);
   if (t == "mlp.up_proj.weight") return glu(1, T_UP);
-  if (t == "mlp.down_proj.weight") return mat(L.wd, H, I, T_DOWN);
+  if (t == "mlp.down_proj.weight") return cols(L.wd, H, I, T_DOWN);
   return fail(B2_ERR_ARG, "unknown tensor name %s", name);
 }
 
@@ -833,7 +996,7 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   c->max_batch = max_batch;
   c->max_tokens = max_tokens;
   c->len = 0;
-  c->plane = static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * max_tokens * e->cfg.head_dim;
+  c->plane = static_cast<size_t>(max_batch) * e->nkv * max_tokens * e->cfg.head_dim;
   c->pf = e->cfg.precise ? 2 : 1;
   const size_t bytes = c->plane * c->pf * 2 * e->cfg.num_hidden_layers * 2;
   if (c->pf == 2 && c->plane > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "precise-mode cache plane too large"); }
@@ -843,10 +1006,10 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
     CK(cudaMalloc(&c->t0_dev, 4));
     CK(cudaMemset(c->t0_dev, 0, 4));
     if (!e->cfg.precise) {
-      c->dec_splits = decode_splits(max_batch, e->cfg.num_key_value_heads, max_tokens);
-      CK(cudaMalloc(&c->dec_part, decode_part_floats(max_batch, e->cfg.num_attention_heads, e->cfg.head_dim) * 4));
-      CK(cudaMalloc(&c->dec_cnt, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
-      CK(cudaMemset(c->dec_cnt, 0, static_cast<size_t>(max_batch) * e->cfg.num_key_value_heads * 4));
+      c->dec_splits = decode_splits(max_batch, e->nkv, max_tokens);
+      CK(cudaMalloc(&c->dec_part, decode_part_floats(max_batch, e->nh, e->cfg.head_dim) * 4));
+      CK(cudaMalloc(&c->dec_cnt, static_cast<size_t>(max_batch) * e->nkv * 4));
+      CK(cudaMemset(c->dec_cnt, 0, static_cast<size_t>(max_batch) * e->nkv * 4));
     }
     CK(cudaDeviceSynchronize());       // cudaMemset is asynchronous; callers may use non-blocking streams
     return B2_OK;
@@ -887,7 +1050,7 @@ extern "C" int b2_cache_read(const b2_cache* c, int layer, int which, int batch,
   // [batch*NKV] slabs of [len, HD] out of [max_tokens, HD]
   CK(cudaMemcpy2DAsync(dev_out, static_cast<size_t>(c->len) * g.head_dim * 2, src,
                        static_cast<size_t>(c->max_tokens) * g.head_dim * 2, static_cast<size_t>(c->len) * g.head_dim * 2,
-                       static_cast<size_t>(batch) * g.num_key_value_heads, cudaMemcpyDeviceToDevice, 0));
+                       static_cast<size_t>(batch) * c->e->nkv, cudaMemcpyDeviceToDevice, 0));
   CK(cudaDeviceSynchronize());
   return B2_OK;
 }
@@ -900,10 +1063,10 @@ static int ensure_ws(b2_engine* e, int M, int B) {
   CK(cudaStreamSynchronize(e->stream));
   free_ws(e);
   const b2_config& c = e->cfg;
-  const size_t H = c.hidden_size, I = c.intermediate_size;
+  const size_t H = c.hidden_size, I = e->I;
   const size_t Mp = M > e->ws_tokens ? M : e->ws_tokens, Bp = B > e->ws_batch ? B : e->ws_batch;
   CK(cudaMalloc(&e->x, Mp * H * 4));
-  if (c.gemma) CK(cudaMalloc(&e->y, Mp * H * 4));
+  if (c.gemma || e->tp_world > 1) CK(cudaMalloc(&e->y, Mp * H * 4));   // tp: partial sums of the row-parallel GEMMs
   const size_t pf = c.precise ? 2 : 1;   // precise mode: every bf16 activation row is [hi | lo]
   CK(cudaMalloc(&e->xn, Mp * H * 2 * pf));
   CK(cudaMalloc(&e->q, Mp * e->q_cols * 2 * pf));
@@ -913,24 +1076,48 @@ static int ensure_ws(b2_engine* e, int M, int B) {
   CK(cudaMalloc(&e->xl, Bp * H * 4));
   CK(cudaMalloc(&e->part, static_cast<size_t>(MAX_SPLIT) * 128 * H * 4));
   CK(cudaMalloc(&e->xnl, Bp * H * 2 * pf));
+  CK(cudaMalloc(&e->ss, static_cast<size_t>(SK_MAX_ROWS) * (H / 32) * 4));
   e->ws_tokens = static_cast<int>(Mp);
   e->ws_batch = static_cast<int>(Bp);
   return B2_OK;
 }
 
 // nsplit > 0: first fold the pending split-K partials of the previous o_proj / down_proj into x
-static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16* ob, float* of, int M, int nsplit = 0) {
+// Partial sums still to be folded into the residual stream x by the next norm kernel: `n` planes of [rows, H] fp32,
+// `stride` floats apart, starting at `src` -- split-K partials of a skinny o_proj / down_proj (summed in plane order:
+// deterministic), or the single all-reduced partial of a row-parallel GEMM under tensor parallelism.
+struct Fold {
+  const float* src = nullptr;
+  int n = 0;
+  size_t stride = 0;
+};
+
+static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16* ob, float* of, int M, Fold f = Fold()) {
   const int H = e->cfg.hidden_size, pf = e->cfg.precise ? 2 : 1;
   const int ld = pf * H, lo = e->cfg.precise ? H : 0;   // precise: [hi | lo] rows
   e->st.launches++;
   if (M <= 128) {   // decode / tiny prompts: a CTA per row keeps every load of the row in flight
     CK(launch_k(rmsnorm_row_kernel, dim3(M), dim3(256), 0, st, x, g, ob, ld, lo, of, H, e->cfg.rms_norm_eps,
-                static_cast<const float*>(e->part), nsplit, static_cast<size_t>(128) * H));
+                f.src, f.n, f.stride));
     return B2_OK;
   }
-  if (nsplit) return fail(B2_ERR_STATE, "split-K partials are only folded on the few-row path");
-  CK(launch_k(rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, static_cast<const float*>(x), g, ob, ld, lo, of, M, H,
-              e->cfg.rms_norm_eps));
+  if (f.n > 1) return fail(B2_ERR_STATE, "split-K partials are only folded on the few-row path");
+  CK(launch_k(rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, f.n ? f.src : static_cast<const float*>(nullptr), g, ob, ld, lo,
+              of, M, H, e->cfg.rms_norm_eps));
+  return B2_OK;
+}
+
+// sum over the tensor-parallel ranks, in place (NCCL over NVLink / NVSwitch)
+static int tp_allreduce(b2_engine* e, cudaStream_t st, float* buf, size_t count) {
+  if (e->tp_world <= 1) return B2_OK;
+  if (!e->comm) return fail(B2_ERR_STATE, "tensor-parallel engine used before b2_tp_init");
+  time_begin(e, st, 0.0, 2);
+  ncclResult_t r = nccl_api()->AllReduce(buf, buf, count, ncclFloat, ncclSum, e->comm, st);
+  time_end(e, st);
+  if (r != ncclSuccess) return fail(B2_ERR_CUDA, "ncclAllReduce failed: %s", nccl_api()->GetErrorString(r));
+  e->comm_calls++;
+  e->comm_bytes += static_cast<double>(count) * 4;
+  e->st.launches++;
   return B2_OK;
 }
 
@@ -976,16 +1163,124 @@ struct FwdArgs {
   float* attn_probs = nullptr;      // [L,B,NH,S,T] opt-in materialisation of the reference's `attentions` (:713-714)
 };
 
+// o_proj / down_proj (Linear_np + the residual add, llama3.2_model_numpy.py:514 + :569, :176-182 + :578): A [M,K] . W[H,K]^T.
+// Four shapes of the same thing; what is left for the following norm kernel to fold into x comes back in `f`:
+//   prefill, 1 GPU (Llama)   x += A.W^T by the GEMM's own TMA reduce-add epilogue                       f = {}
+//   few rows (decode)        split-K partial planes in e->part (all SMs stream weights)                  f = {part, ns, stride}
+//   tensor parallel          this rank's partial sum -> ncclAllReduce over the ranks                     f = {y or part, ...}
+//   Gemma-2                  y is needed on its own (post-norm before the residual add), never EPI_RESID f = {y or part, ...}
+static int row_parallel_proj(b2_engine* e, cudaStream_t st, const bf16* a, int K, const bf16* w, int M, bool skinny, Fold& f) {
+  const b2_config& c = e->cfg;
+  const int H = c.hidden_size;
+  const bool tp = e->tp_world > 1;
+  GemmParams p = base_params(M, H, K);
+  f = Fold();
+  if (skinny) {
+    const int sr = tp ? ((M + 31) / 32) * 32 : 128;      // tp: planes packed back to back so one all-reduce covers them
+    p.out = e->part; p.ldo = H; p.split_rows = sr;
+    p.split_k = pick_split(H, K, 64);
+    CKR(eng_gemm(e, st, 64, EPI_F32, a, K, w, p, 0, MAX_SPLIT * 128));
+    f.src = e->part; f.n = p.split_k; f.stride = static_cast<size_t>(sr) * H;
+    if (tp) CKR(tp_allreduce(e, st, e->part, static_cast<size_t>(p.split_k) * sr * H));
+    return B2_OK;
+  }
+  if (!c.gemma && !tp) {
+    p.out = e->x; p.ldo = H;
+    return eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, a, K, w, p);
+  }
+  p.out = e->y; p.ldo = H;
+  CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, a, K, w, p));
+  if (tp) CKR(tp_allreduce(e, st, e->y, static_cast<size_t>(M) * H));
+  f.src = e->y; f.n = 1; f.stride = 0;
+  return B2_OK;
+}
+
+// One-token decode step (S == 1, <= 64 sequences, Llama) with the RMSNorm split across the GEMMs and the split-K
+// reduction done inside thread-block clusters (gemm_sk_tcgen05.cuh): 5 kernels per layer
+//   QKV(+1/rms, RoPE, append) -> attention -> o_proj(+residual, x*gamma, sum x^2) -> gate/up(+1/rms, SiLU*up) ->
+//   down_proj(+residual, x*gamma', sum x^2)
+// instead of 7 (two RMSNorm kernels folding split-K partial planes).  Same arithmetic as the reference's layer
+// (llama3.2_model_numpy.py:554-578); the norm's 1/sqrt(mean(x^2)+eps) is applied to the fp32 accumulators of the
+// consuming GEMM instead of to its bf16 operand.  B2_NO_FUSED_DECODE=1 selects the 7-kernel path.
+static bool fused_decode_ok(const b2_engine* e, const FwdArgs& fa) {
+  static const bool off = getenv("B2_NO_FUSED_DECODE") != nullptr;
+  const b2_config& c = e->cfg;
+  return !off && fa.S == 1 && fa.B <= SK_MAX_ROWS && fa.ids && !fa.hidden && !fa.attn_probs && !c.gemma && !c.precise &&
+         e->tp_world == 1 && c.hidden_size % 64 == 0 && e->q_cols % 64 == 0 && e->I % 64 == 0 &&
+         fa.logits_mode != B2_LOGITS_NONE;
+}
+
+static int run_decode_fused(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdArgs& fa) {
+  const b2_config& c = e->cfg;
+  const int M = fa.B, H = c.hidden_size, I = e->I, L = c.num_hidden_layers, HD = c.head_dim;
+  const int ss_n = H / 32;
+  auto consumer = [&](GemmParams& p) {   // this GEMM's A operand is x*gamma: scale its rows by 1/rms(x)
+    p.ss_in = e->ss; p.ss_n = ss_n; p.norm_dim = H; p.norm_eps = c.rms_norm_eps;
+  };
+  CK(launch_k(embed_norm_row_kernel, dim3(M), dim3(256), 0, st, reinterpret_cast<const long long*>(fa.ids),
+              static_cast<const bf16*>(e->embed), e->x, e->xn, static_cast<const float*>(e->layers[0].g_in), e->ss, ss_n, H,
+              c.vocab_size, 1.0f));
+  e->st.launches++;
+  const float scale = c.attn_scale > 0.f ? c.attn_scale : 1.0f / sqrtf(static_cast<float>(HD));
+  for (int li = 0; li < L; ++li) {
+    Layer& Ly = e->layers[li];
+    {
+      GemmParams p = base_params(M, e->qkv_n, H);
+      p.q_cols = e->q_cols; p.kv_cols = e->kv_cols; p.head_dim = HD; p.S = 1; p.Tmax = cache->max_tokens; p.nkv = e->nkv;
+      p.q_out = e->q; p.ldq = e->q_cols;
+      p.k_cache = cache_k(cache, li); p.v_cache = cache_v(cache, li);
+      p.t0_ptr = cache->t0_dev; p.pos_ids = fa.pos_ids; p.rope_cos = e->rope_cos; p.rope_sin = e->rope_sin;
+      consumer(p);
+      if (HD == SK_BN) CKR(eng_gemm_sk(e, st, EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
+      else CKR(eng_gemm(e, st, HD, EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
+    }
+    const int window = (c.sliding_window > 0 && e->sliding[li]) ? c.sliding_window : 0;
+    CKR(attn_decode(e->q, e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, e->q_cols, M, e->nh, e->nkv, HD,
+                    cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st, 0, 0, 0, cache->dec_part,
+                    cache->dec_cnt, cache->dec_splits));
+    e->st.launches++;
+    {
+      GemmParams p = base_params(M, H, e->q_cols);          // x += attn . Wo^T; xn = bf16(x * g_post); ss
+      p.out = e->x; p.ldo = H; p.a_out = e->xn; p.gamma_next = Ly.g_post_attn; p.ss_out = e->ss;
+      CKR(eng_gemm_sk(e, st, EPI_RESID_NORM, e->att, e->q_cols, Ly.wo, p));
+    }
+    {
+      GemmParams p = base_params(M, 2 * I, H);
+      p.out = e->hb; p.ldo = I; p.act = c.hidden_act;
+      consumer(p);
+      const int bn_glu = ((2 * I) / 128 <= e->n_sms) ? 128 : 64;
+      CKR(eng_gemm(e, st, bn_glu, EPI_GLU, e->xn, H, Ly.wgu, p));
+    }
+    {
+      GemmParams p = base_params(M, H, I);                  // x += h . Wd^T; xn = bf16(x * g_in[next] | g_final); ss
+      p.out = e->x; p.ldo = H; p.a_out = e->xn; p.ss_out = e->ss;
+      p.gamma_next = (li + 1 < L) ? e->layers[li + 1].g_in : e->g_final;
+      CKR(eng_gemm_sk(e, st, EPI_RESID_NORM, e->hb, I, Ly.wd, p));
+    }
+  }
+  {   // lm_head on the last down_proj's x * g_final (tied embedding, :1025-1026); S == 1: ALL and LAST are the same rows
+    GemmParams p = base_params(M, e->V, H);
+    p.out = fa.logits; p.ldo = e->V; p.softcap = c.final_logit_softcap;
+    consumer(p);
+    CKR(eng_gemm(e, st, 128, EPI_F32, e->xn, H, e->embed, p, e->ws_tokens));
+  }
+  CK(launch_k(add_scalar_kernel, dim3(1), dim3(32), 0, st, cache->t0_dev, 1));
+  e->st.launches++;
+  return B2_OK;
+}
+
 static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdArgs& fa) {
+  if (fused_decode_ok(e, fa)) return run_decode_fused(e, cache, st, fa);
   const b2_config& c = e->cfg;
   const int B = fa.B, S = fa.S, logits_mode = fa.logits_mode;
   float* const logits = fa.logits;
   float* const hidden = fa.hidden;
-  const int M = B * S, H = c.hidden_size, I = c.intermediate_size, L = c.num_hidden_layers, HD = c.head_dim;
+  const int M = B * S, H = c.hidden_size, I = e->I, L = c.num_hidden_layers, HD = c.head_dim;
   const bool decode = (S == 1);
+  const bool tp = e->tp_world > 1;
   const int pf = c.precise ? 2 : 1;            // bf16 activation rows are [hi | lo] in precise mode
   const bool skinny = M <= 128 && !hidden;     // few rows: split-K so the weight stream covers all SMs
-  int pend = 0;                                // split-K partials of the last down_proj not yet folded into x
+  Fold pend;                                   // partial sums of the last down_proj not yet folded into x
   const float escale = c.gemma ? sqrtf(static_cast<float>(H)) : 1.0f;
   if (fa.embeds) {   // hidden_states = inputs_embeds (* sqrt(H) for Gemma-2, gemma2_model.py:738-739)
     CK(launch_k(scale_copy_kernel, dim3(2 * e->n_sms), dim3(256), 0, st, fa.embeds, e->x, static_cast<size_t>(M) * H / 4, escale));
@@ -999,17 +1294,20 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
   const int T_total = cache->len + S;
   for (int li = 0; li < L; ++li) {
     Layer& Ly = e->layers[li];
-    if (hidden) CK(cudaMemcpyAsync(hidden + static_cast<size_t>(li) * M * H, e->x, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
+    if (hidden) {
+      if (pend.n) return fail(B2_ERR_STATE, "internal: hidden-state capture with unfolded partial sums");
+      CK(cudaMemcpyAsync(hidden + static_cast<size_t>(li) * M * H, e->x, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
+    }
     CKR(rmsnorm(e, st, e->x, Ly.g_in, e->xn, nullptr, M, pend));
-    pend = 0;
-    {  // fused QKV projection + RoPE + KV-cache append
+    pend = Fold();
+    {  // fused QKV projection + RoPE + KV-cache append (column-parallel under tp: this rank's heads)
       GemmParams p = base_params(M, e->qkv_n, H);
       p.q_cols = e->q_cols;
       p.kv_cols = e->kv_cols;
       p.head_dim = HD;
       p.S = S;
       p.Tmax = cache->max_tokens;
-      p.nkv = c.num_key_value_heads;
+      p.nkv = e->nkv;
       p.q_out = e->q;
       p.ldq = pf * e->q_cols;
       p.lo_off = c.precise ? e->q_cols : 0;
@@ -1027,66 +1325,46 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
     // HF Gemma-2: only the layers whose layer_types entry is "sliding_attention" slide (default pattern: even layers)
     const int window = (c.sliding_window > 0 && e->sliding[li]) ? c.sliding_window : 0;
     if (fa.attn_probs) {   // debug: this layer's [B,NH,S,T] softmax probabilities, recomputed from q and the K cache
-      const size_t rows = static_cast<size_t>(B) * c.num_attention_heads * S;
+      const size_t rows = static_cast<size_t>(B) * e->nh * S;
       CK(launch_k(attn_probs_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, st, static_cast<const bf16*>(e->q),
                   pf * e->q_cols, static_cast<const bf16*>(cache_k(cache, li)), fa.attn_probs + static_cast<size_t>(li) * rows * T_total,
-                  B, S, c.num_attention_heads, c.num_key_value_heads, HD, cache->max_tokens, static_cast<const int*>(cache->t0_dev),
+                  B, S, e->nh, e->nkv, HD, cache->max_tokens, static_cast<const int*>(cache->t0_dev),
                   scale, c.attn_logit_softcap, causal, window));
       e->st.launches++;
     }
     if (decode) {
-      CKR(attn_decode(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, pf * e->q_cols, B, c.num_attention_heads,
-                      c.num_key_value_heads, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st,
+      CKR(attn_decode(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, pf * e->q_cols, B, e->nh,
+                      e->nkv, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st,
                       c.precise ? e->q_cols : 0, c.precise ? cache->plane : 0, c.precise ? e->q_cols : 0, cache->dec_part,
                       cache->dec_cnt, cache->dec_splits));
       e->st.launches++;
     } else {
       AttnParams a;
       memset(&a, 0, sizeof(a));
-      a.B = B; a.S = S; a.NH = c.num_attention_heads; a.NKV = c.num_key_value_heads; a.Tmax = cache->max_tokens;
+      a.B = B; a.S = S; a.NH = e->nh; a.NKV = e->nkv; a.Tmax = cache->max_tokens;
       a.t0_ptr = cache->t0_dev; a.scale = scale; a.softcap = c.attn_logit_softcap; a.causal = causal; a.window = window;
       a.out = e->att; a.ldo = pf * e->q_cols;
       if (c.precise) {
         a.q_lo_col = e->q_cols;
         a.out_lo_col = e->q_cols;
-        a.kv_lo_row = cache->max_batch * c.num_key_value_heads * cache->max_tokens;
+        a.kv_lo_row = cache->max_batch * e->nkv * cache->max_tokens;
       }
       const double T = cache->len + S;
       const double pairs = causal ? (static_cast<double>(S) * (S + 1) / 2 + static_cast<double>(S) * cache->len) : S * T;
-      time_begin(e, st, 4.0 * B * c.num_attention_heads * HD * pairs, 1);
+      time_begin(e, st, 4.0 * B * e->nh * HD * pairs, 1);
       int r = attn_prefill(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), a, HD, st);
       time_end(e, st);
       CKR(r);
       e->st.launches++;
       e->st.attn_launches++;
     }
+    Fold f;
+    CKR(row_parallel_proj(e, st, e->att, e->q_cols, Ly.wo, M, skinny, f));                // attn . Wo^T
     if (!c.gemma) {
-      GemmParams p = base_params(M, H, e->q_cols);
-      int ns = 0;
-      if (skinny) {   // split-K partials, summed in fixed order by the norm that follows (deterministic)
-        p.out = e->part; p.ldo = H; p.split_rows = 128;
-        p.split_k = ns = pick_split(H, e->q_cols, 64);
-        CKR(eng_gemm(e, st, 64, EPI_F32, e->att, e->q_cols, Ly.wo, p, 0, MAX_SPLIT * 128));
-      } else {
-        p.out = e->x; p.ldo = H;
-        CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->att, e->q_cols, Ly.wo, p));   // x += attn . Wo^T
-      }
-      CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M, ns));
-    } else {
-      GemmParams p = base_params(M, H, e->q_cols);
-      const float* ysrc = e->y;
-      int ns = 1;
-      if (skinny) {
-        p.out = e->part; p.ldo = H; p.split_rows = 128;
-        p.split_k = ns = pick_split(H, e->q_cols, 64);
-        ysrc = e->part;
-        CKR(eng_gemm(e, st, 64, EPI_F32, e->att, e->q_cols, Ly.wo, p, 0, MAX_SPLIT * 128));
-      } else {
-        p.out = e->y; p.ldo = H;
-        CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->att, e->q_cols, Ly.wo, p));
-      }
-      CK(launch_k(add_rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->x, ysrc, static_cast<const float*>(Ly.g_post_attn), M, H,
-                  c.rms_norm_eps, ns, static_cast<size_t>(128) * H));
+      CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M, f));                     // x += ...; xn = norm(x)
+    } else {   // Gemma-2: x += post_attention_norm(attn_out); xn = pre_feedforward_norm(x)  (gemma2_model.py:623-641)
+      CK(launch_k(add_rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->x, f.src, static_cast<const float*>(Ly.g_post_attn), M, H,
+                  c.rms_norm_eps, f.n, f.stride));
       e->st.launches++;
       CKR(rmsnorm(e, st, e->x, Ly.g_pre_ffn, e->xn, nullptr, M));
     }
@@ -1098,53 +1376,69 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
       const int bn_glu = (M <= 128 && (2 * I) / 128 <= e->n_sms) ? 128 : pick_bn(M, 2 * I, 0);
       CKR(eng_gemm(e, st, bn_glu, EPI_GLU, e->xn, H, Ly.wgu, p));                          // act(gate)*up
     }
+    CKR(row_parallel_proj(e, st, e->hb, I, Ly.wd, M, skinny, f));                          // h . Wd^T
     if (!c.gemma) {
-      GemmParams p = base_params(M, H, I);
-      if (skinny) {
-        p.out = e->part; p.ldo = H; p.split_rows = 128;
-        p.split_k = pend = pick_split(H, I, 64);      // folded into x by the next layer's input norm / the final norm
-        CKR(eng_gemm(e, st, 64, EPI_F32, e->hb, I, Ly.wd, p, 0, MAX_SPLIT * 128));
-      } else {
-        p.out = e->x; p.ldo = H;
-        CKR(eng_gemm(e, st, M <= 128 ? 32 : 256, EPI_RESID, e->hb, I, Ly.wd, p));            // x += h . Wd^T
+      pend = f;                  // folded into x by the next layer's input norm / the final norm
+      if (hidden && pend.n) {    // hidden-state capture copies x at the top of the next layer: fold now
+        CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M, pend));
+        pend = Fold();
       }
     } else {
-      GemmParams p = base_params(M, H, I);
-      const float* ysrc = e->y;
-      int ns = 1;
-      if (skinny) {
-        p.out = e->part; p.ldo = H; p.split_rows = 128;
-        p.split_k = ns = pick_split(H, I, 64);
-        ysrc = e->part;
-        CKR(eng_gemm(e, st, 64, EPI_F32, e->hb, I, Ly.wd, p, 0, MAX_SPLIT * 128));
-      } else {
-        p.out = e->y; p.ldo = H;
-        CKR(eng_gemm(e, st, pick_bn(M, H, 0), EPI_F32, e->hb, I, Ly.wd, p));
-      }
-      CK(launch_k(add_rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->x, ysrc, static_cast<const float*>(Ly.g_post_ffn), M, H,
-                  c.rms_norm_eps, ns, static_cast<size_t>(128) * H));
+      CK(launch_k(add_rmsnorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->x, f.src, static_cast<const float*>(Ly.g_post_ffn), M, H,
+                  c.rms_norm_eps, f.n, f.stride));
       e->st.launches++;
     }
   }
-  // final norm + lm_head (tied to the embedding, llama3.2_model_numpy.py:1025-1026)
+  // final norm + lm_head (tied to the embedding, llama3.2_model_numpy.py:1025-1026); vocabulary-parallel under tp
   float* hid_last = hidden ? hidden + static_cast<size_t>(L) * M * H : nullptr;
+  const bf16* wlm = e->embed + static_cast<size_t>(e->tp_rank) * e->V * H;
+  const int Vl = e->V;
+  auto lm_head = [&](const bf16* a, int rows, int a_rows) -> int {
+    GemmParams p = base_params(rows, Vl, H);
+    p.softcap = c.final_logit_softcap;
+    if (!tp) {
+      p.out = logits; p.ldo = Vl;
+      return eng_gemm(e, st, rows <= 128 ? 128 : 256, EPI_F32, a, H, wlm, p, a_rows);
+    }
+    const size_t loc = static_cast<size_t>(rows) * Vl;
+    if (loc * (1 + e->tp_world) > e->tp_lg_elems) {
+      if (e->capturing) return fail(B2_ERR_STATE, "tp logits scratch must be sized before graph capture");
+      CK(cudaStreamSynchronize(st));
+      cudaFree(e->tp_lg);
+      e->tp_lg = nullptr;
+      e->tp_lg_elems = 0;
+      CK(cudaMalloc(&e->tp_lg, loc * (1 + e->tp_world) * 4));
+      e->tp_lg_elems = loc * (1 + e->tp_world);
+    }
+    float* gathered = e->tp_lg + loc;
+    p.out = e->tp_lg; p.ldo = Vl;
+    CKR(eng_gemm(e, st, rows <= 128 ? 128 : 256, EPI_F32, a, H, wlm, p, a_rows));
+    time_begin(e, st, 0.0, 2);
+    ncclResult_t r = nccl_api()->AllGather(e->tp_lg, gathered, loc, ncclFloat, e->comm, st);
+    time_end(e, st);
+    if (r != ncclSuccess) return fail(B2_ERR_CUDA, "ncclAllGather failed: %s", nccl_api()->GetErrorString(r));
+    e->comm_calls++;
+    e->comm_bytes += static_cast<double>(loc) * 4 * e->tp_world;
+    CK(launch_k(tp_unshard_logits_kernel, dim3(4 * e->n_sms), dim3(256), 0, st, static_cast<const float*>(gathered), logits, rows, Vl,
+                e->tp_world));
+    e->st.launches += 2;
+    return B2_OK;
+  };
   if (logits_mode == B2_LOGITS_ALL || hidden) {
     CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, hid_last, M, pend));
-    pend = 0;
+    pend = Fold();
   }
   if (logits_mode == B2_LOGITS_ALL) {
-    GemmParams p = base_params(M, c.vocab_size, H);
-    p.out = logits; p.ldo = c.vocab_size; p.softcap = c.final_logit_softcap;
-    CKR(eng_gemm(e, st, M <= 128 ? 128 : 256, EPI_F32, e->xn, H, e->embed, p));
+    CKR(lm_head(e->xn, M, 0));
   } else if (logits_mode == B2_LOGITS_LAST) {
     const bf16* a = e->xn;
     int lda_rows = 0;
     if (S == 1) {
       if (!hidden) CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, nullptr, M, pend));
     } else {
-      if (pend) {   // fold the last down_proj partials into x before gathering rows (xn output unused here)
+      if (pend.n) {   // fold the last down_proj partials into x before gathering rows (xn output unused here)
         CKR(rmsnorm(e, st, e->x, e->g_final, e->xn, nullptr, M, pend));
-        pend = 0;
+        pend = Fold();
       }
       CK(launch_k(gather_last_kernel, dim3(B), dim3(256), 0, st, static_cast<const float*>(e->x), e->xl, B, S, H));
       e->st.launches++;
@@ -1152,9 +1446,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
       a = e->xnl;
       lda_rows = 1;
     }
-    GemmParams p = base_params(B, c.vocab_size, H);
-    p.out = logits; p.ldo = c.vocab_size; p.softcap = c.final_logit_softcap;
-    CKR(eng_gemm(e, st, B <= 128 ? 128 : 256, EPI_F32, a, H, e->embed, p, lda_rows ? e->ws_batch : e->ws_tokens));
+    CKR(lm_head(a, B, lda_rows ? e->ws_batch : e->ws_tokens));
   }
   CK(launch_k(add_scalar_kernel, dim3(1), dim3(32), 0, st, cache->t0_dev, S));
   e->st.launches++;
@@ -1260,6 +1552,30 @@ extern "C" int b2_forward(b2_engine* e, b2_cache* cache, const int64_t* ids, int
   return b2_forward_ex(e, cache, &a);
 }
 
+// ------------------------------------------------------------------------------------------
+// tensor parallelism (optional): NCCL communicator over the tp_world engines
+// ------------------------------------------------------------------------------------------
+extern "C" int b2_tp_unique_id(void* id_out) {
+  if (!id_out) return fail(B2_ERR_ARG, "null argument");
+  const NcclApi* n = nccl_api();
+  if (!n) return fail(B2_ERR_STATE, "libnccl.so.2 could not be loaded: %s", dlerror());
+  static_assert(sizeof(ncclUniqueId) == B2_NCCL_ID_BYTES, "ncclUniqueId size");
+  CKN(n->GetUniqueId(static_cast<ncclUniqueId*>(id_out)));
+  return B2_OK;
+}
+extern "C" int b2_tp_init(b2_engine* e, const void* id) {
+  if (!e || !id) return fail(B2_ERR_ARG, "null argument");
+  if (e->tp_world <= 1) return fail(B2_ERR_ARG, "engine was created with tp_world <= 1");
+  if (e->comm) return fail(B2_ERR_STATE, "b2_tp_init called twice");
+  const NcclApi* n = nccl_api();
+  if (!n) return fail(B2_ERR_STATE, "libnccl.so.2 could not be loaded: %s", dlerror());
+  CK(cudaSetDevice(e->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  CKN(n->CommInitRank(&e->comm, e->tp_world, uid, e->tp_rank));
+  return B2_OK;
+}
+
 extern "C" int b2_set_layer_types(b2_engine* e, const int32_t* is_sliding, int n) {
   if (!e || !is_sliding) return fail(B2_ERR_ARG, "null argument");
   if (n != e->cfg.num_hidden_layers) return fail(B2_ERR_ARG, "layer_types has %d entries, the model has %d layers", n, e->cfg.num_hidden_layers);
@@ -1355,6 +1671,8 @@ extern "C" int b2_reset_stats(b2_engine* e) {
   e->st.used.clear();
   e->st.launches = e->st.gemm_launches = e->st.attn_launches = 0;
   e->st.forwards = e->st.timed_forwards = 0;
+  e->comm_calls = 0;
+  e->comm_bytes = 0;
   return B2_OK;
 }
 extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
@@ -1365,13 +1683,16 @@ extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
   out->gemm_launches = e->st.gemm_launches;
   out->attn_launches = e->st.attn_launches;
   out->timed_forwards = e->st.timed_forwards;
+  out->comm_calls = e->comm_calls;
+  out->comm_bytes = e->comm_bytes;
   if (!e->st.used.empty()) {
     CK(cudaDeviceSynchronize());
     for (auto& ev : e->st.used) {
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
       if (ev.kind == 0) { out->gemm_ms += ms; out->gemm_flops += ev.flops; }
-      else { out->attn_ms += ms; out->attn_flops += ev.flops; }
+      else if (ev.kind == 1) { out->attn_ms += ms; out->attn_flops += ev.flops; }
+      else out->comm_ms += ms;
     }
   }
   return B2_OK;
@@ -1383,7 +1704,7 @@ extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
 extern "C" int b2_op_rmsnorm(const float* x, const float* g, void* ob, float* of, int M, int H, float eps, void* stream) {
   CKR(require_gpu(0));
   if (H % 128 || H > 128 * NORM_MAXV) return fail(B2_ERR_ARG, "H=%d must be a multiple of 128 and <= %d", H, 128 * NORM_MAXV);
-  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, static_cast<bf16*>(ob), H, 0, of, M, H, eps);
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(const_cast<float*>(x), nullptr, g, static_cast<bf16*>(ob), H, 0, of, M, H, eps);
   CK(cudaGetLastError());
   return B2_OK;
 }
@@ -1417,6 +1738,23 @@ extern "C" int b2_op_gemm(const void* a, const void* w, void* out, int M, int N,
   if (epi == EPI_F32 || epi == EPI_RESID) CKR(make_tmap_t(&tc, out, M, N, N, 32, true));
   if (two_cta) return launch_gemm2(epi, ta, tb, tc, p, static_cast<cudaStream_t>(stream));
   return launch_gemm(bn, epi, ta, tb, tc, p, static_cast<cudaStream_t>(stream));
+}
+
+// few-row cluster split-K GEMM with the residual + half-norm epilogue (decode step): x[M,N] += a[M,K] . w[N,K]^T;
+// a_out = bf16(x * gamma); ss[M, N/32] = per-32-column sums of x^2.  cluster = CTAs per output tile (0 = engine's choice).
+extern "C" int b2_op_gemm_sk(const void* a, const void* w, float* x, void* a_out, const float* gamma, float* ss, int M, int N, int K,
+                             int cluster, void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CKR(require_gpu(dev));
+  GemmParams p = base_params(M, N, K);
+  p.a_box_rows = M <= 32 ? 32 : 64;
+  p.split_k = cluster > 0 ? cluster : pick_cluster(N / SK_BN, K / GEMM_BK, num_sms());
+  p.out = x; p.ldo = N; p.a_out = static_cast<bf16*>(a_out); p.gamma_next = gamma; p.ss_out = ss;
+  CUtensorMap ta, tb;
+  CKR(make_tmap(&ta, a, M, K, K, p.a_box_rows));
+  CKR(make_tmap(&tb, w, N, K, K, SK_BN));
+  return launch_gemm_sk(EPI_RESID_NORM, ta, tb, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b2_op_qkv_rope(const void* a, const void* w, void* q, void* kc, void* vc, int B, int S, int H, int NH,

@@ -24,7 +24,7 @@
 
 namespace b2 {
 
-enum GemmEpi : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_QKV_ROPE = 3, EPI_GLU = 4 };
+enum GemmEpi : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_QKV_ROPE = 3, EPI_GLU = 4, EPI_RESID_NORM = 5 };
 
 struct GemmParams {
   int M, N, K;   // K = contraction length seen by A (2*k_wrap in hi/lo "precise" mode)
@@ -53,7 +53,31 @@ struct GemmParams {
   int kv_lo_off;           // precise mode: element offset of the lo plane of the caches (0 = none)
   int a_box_rows;          // 1-CTA kernel: rows of A one TMA box brings in (32/64 when M is that small, else 0 = 128);
                            // the remaining rows of the 128-row MMA tile are zeroed once instead of fetched every k-step
+  // ---- RMSNorm split across two GEMMs (decode step; LlamaRMSNorm_np, llama3.2_model_numpy.py:256-278):
+  //   producer (EPI_RESID_NORM): x += acc (fp32, in place); a_out = bf16(x * gamma_next); ss_out[row][32-column block]
+  //                              = sum of x^2 over that block -- "x * gamma" now, "* 1/sqrt(mean(x^2)+eps)" later
+  //   consumer (ss_in != nullptr, EPI_QKV_ROPE / EPI_GLU / EPI_F32): its A operand is such an a_out; every accumulator
+  //                              row is scaled by rs = 1/sqrt(sum(ss_in[row][0..ss_n)) / norm_dim + eps) first (the GEMM is
+  //                              linear in its rows, so scaling after the contraction equals normalising before it)
+  __nv_bfloat16* a_out;    // [M, N] bf16
+  const float* gamma_next; // [N]
+  float* ss_out;           // [M, N/32]
+  const float* ss_in;      // [M, ss_n]
+  int ss_n, norm_dim;
+  float norm_eps;
 };
+
+// 1/sqrt(mean(x^2) + eps) of a row whose partial sums of squares were left by an EPI_RESID_NORM producer (or by
+// embed_norm_row_kernel); fixed summation order => deterministic and independent of the batch neighbours
+__device__ __forceinline__ float row_rs(const GemmParams& p, int row) {
+  const float* s = p.ss_in + static_cast<size_t>(row) * p.ss_n;
+  float t = 0.f;
+  for (int i = 0; i < p.ss_n; i += 4) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(s + i));
+    t += (v.x + v.y) + (v.z + v.w);
+  }
+  return 1.0f / sqrtf(t / static_cast<float>(p.norm_dim) + p.norm_eps);
+}
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -109,6 +133,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
   if constexpr (EPI == EPI_F32 || EPI == EPI_RESID) {
     // registers -> swizzled smem slab (row = lane, 16-byte chunk j at j ^ (lane & 7)) -> TMA store / reduce-add
     const float inv_cap = p.softcap > 0.f ? 1.0f / p.softcap : 0.f;
+    const float rs = (EPI == EPI_F32 && p.ss_in && row_ok) ? row_rs(p, row) : 1.0f;
 #pragma unroll 1
     for (int c = half; c < BN / 32; c += 2) {
       const int col = col0 + c * 32;
@@ -116,6 +141,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
       uint32_t r[32];
       tmem_ld32(trow + c * 32, r);
       tmem_ld_wait();
+      if (EPI == EPI_F32 && p.ss_in) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
+      }
       if (EPI == EPI_F32 && p.softcap > 0.f) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(p.softcap * tanhf(__uint_as_float(r[i]) * inv_cap));
@@ -158,6 +187,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
   } else if constexpr (EPI == EPI_GLU) {
     // W rows are interleaved in 32-row groups: [gate 32j..32j+31 | up 32j..32j+31] -> column chunk 2j is
     // gate, chunk 2j+1 is up, output column = N/2-space (col0/2 + 32j).
+    const float rs = (p.ss_in && row_ok) ? row_rs(p, row) : 1.0f;
 #pragma unroll 1
     for (int j = half; j < BN / 64; j += 2) {
       const int col = col0 + j * 64;
@@ -171,9 +201,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float gv = __uint_as_float(g[i]);
+        const float gv = __uint_as_float(g[i]) * rs;
         const float a = p.act == 0 ? act_silu(gv) : act_gelu_tanh(gv);
-        v[i] = a * __uint_as_float(u[i]);
+        v[i] = a * (__uint_as_float(u[i]) * rs);
       }
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + (col >> 1);
       store_bf16x32(o, v);
@@ -182,6 +212,39 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
         split_lo(v, lo);
         store_bf16x32(o + p.lo_off, lo);
       }
+    }
+  } else if constexpr (EPI == EPI_RESID_NORM) {
+    // x += acc; a' = bf16(x * gamma_next); ss[row][column block] = sum x^2   (row = lane: each thread owns 32 columns of its row)
+    float* xout = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+    for (int c = half; c < BN / 32; c += 2) {
+      const int col = col0 + c * 32;
+      if (col >= p.N) break;
+      __syncwarp();
+      uint32_t r[32];
+      tmem_ld32(trow + c * 32, r);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float4* xr = reinterpret_cast<float4*>(xout + static_cast<size_t>(row) * p.ldo + col);
+      const float4* g4 = reinterpret_cast<const float4*>(p.gamma_next + col);
+      float v[32], ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 xv = xr[j];
+        xv.x += __uint_as_float(r[4 * j]);
+        xv.y += __uint_as_float(r[4 * j + 1]);
+        xv.z += __uint_as_float(r[4 * j + 2]);
+        xv.w += __uint_as_float(r[4 * j + 3]);
+        xr[j] = xv;
+        ss += (xv.x * xv.x + xv.y * xv.y) + (xv.z * xv.z + xv.w * xv.w);
+        const float4 gg = __ldg(g4 + j);
+        v[4 * j] = xv.x * gg.x;
+        v[4 * j + 1] = xv.y * gg.y;
+        v[4 * j + 2] = xv.z * gg.z;
+        v[4 * j + 3] = xv.w * gg.w;
+      }
+      store_bf16x32(p.a_out + static_cast<size_t>(row) * p.N + col, v);
+      p.ss_out[static_cast<size_t>(row) * (p.N / 32) + (col >> 5)] = ss;
     }
   } else {  // EPI_QKV_ROPE
     const int HD = p.head_dim;
@@ -195,6 +258,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
     // work items: (head hh, half-chunk i); this warp takes the items of its parity
     float4 cs4[8], sn4[8];   // cos/sin of this row's position for half-chunk tab_i (reused across the heads of a tile)
     int tab_i = -1;
+    // row scale of a split RMSNorm (decode step only: few-row tiles; the 256-wide prefill instantiations skip it)
+    constexpr bool SCALE = BN <= 128;
+    const float rs = (SCALE && p.ss_in && row_ok) ? row_rs(p, row) : 1.0f;
 #pragma unroll 1
     for (int t = half; t < BN / 64; t += 2) {
       const int hh = t / half_chunks, i = t - hh * half_chunks;
@@ -230,6 +296,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
         for (int j = 0; j < 8; ++j) {
           cs4[j] = __ldg(c4 + j);
           sn4[j] = __ldg(s4 + j);
+          if (SCALE) {   // fold 1/rms into the rotation: (p * rs) * cos == p * (rs * cos)
+            cs4[j].x *= rs; cs4[j].y *= rs; cs4[j].z *= rs; cs4[j].w *= rs;
+            sn4[j].x *= rs; sn4[j].y *= rs; sn4[j].z *= rs; sn4[j].w *= rs;
+          }
         }
         tab_i = i;
       }
@@ -252,8 +322,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          x1[j] = __uint_as_float(a[j]);
-          x2[j] = __uint_as_float(c[j]);
+          x1[j] = SCALE ? __uint_as_float(a[j]) * rs : __uint_as_float(a[j]);
+          x2[j] = SCALE ? __uint_as_float(c[j]) * rs : __uint_as_float(c[j]);
         }
       }
       store_bf16x32(dst + i * 32, x1);

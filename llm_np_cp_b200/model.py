@@ -142,7 +142,7 @@ class _CausalLM:
     def __init__(self, config, weights_dict: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
                  max_positions: Optional[int] = None, *, attn_logit_softcapping=None, sliding_window=None,
                  use_query_pre_attn_scalar: bool = False, always_causal: bool = False, precise: bool = False,
-                 rope_scaling: Optional[dict] = None):
+                 rope_scaling: Optional[dict] = None, tensor_parallel: bool = False, tp_group=None):
         self.config = config
         L = _lib.lib()
         if L.b2_device_count() == 0:
@@ -185,12 +185,31 @@ class _CausalLM:
             c.rope_low_freq_factor = float(rope_scaling.get("low_freq_factor", 1.0))
             c.rope_high_freq_factor = float(rope_scaling.get("high_freq_factor", 4.0))
             c.rope_original_max_positions = int(rope_scaling.get("original_max_position_embeddings", 8192))
+        # optional tensor parallelism (BASELINE.json north_star; the reference has none): this process is one rank of an
+        # initialised torch.distributed group, one process per GPU; heads / FFN columns / vocabulary rows are split, the
+        # partial sums of o_proj and down_proj are all-reduced with NCCL inside the engine
+        self.tp_rank, self.tp_world = 0, 1
+        if tensor_parallel:
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("tensor_parallel=True needs an initialised torch.distributed process group (torchrun)")
+            self.tp_rank, self.tp_world = dist.get_rank(tp_group), dist.get_world_size(tp_group)
+            c.tp_rank, c.tp_world = self.tp_rank, self.tp_world
         self._cfg = c
         self.device = torch.device("cuda", device)
         self.vocab_size = c.vocab_size
         h = C.c_void_p()
         check(L.b2_engine_create(C.byref(c), device, C.byref(h)))
         self._h = h
+        if self.tp_world > 1:
+            import torch.distributed as dist
+            uid = (C.c_uint8 * 128)()
+            if self.tp_rank == 0:
+                check(L.b2_tp_unique_id(uid))
+            box = [bytes(uid)]
+            src = dist.get_global_rank(tp_group, 0) if tp_group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=tp_group, device=self.device)
+            check(L.b2_tp_init(self._h, box[0]))      # ncclCommInitRank: collective over the group
         self._graph_on = False
         self._step_logits, self._step_ids = {}, {}
         src = weights_dict if weights_dict is not None else weights
@@ -291,6 +310,8 @@ class _CausalLM:
             hidden = torch.empty((Lc + 1, B, S, H), dtype=torch.float32, device=self.device)
         T = (kv_cache.num_items() if kv_cache is not None else 0) + S
         if output_attentions and self.materialize_attentions:
+            if self.tp_world > 1:
+                raise NotImplementedError("materialize_attentions is a single-GPU debug path")
             probs = torch.empty((Lc, B, self._cfg.num_attention_heads, S, T), dtype=torch.float32, device=self.device)
         a = B2ForwardArgs()
         a.ids = ids.data_ptr() if ids is not None else None

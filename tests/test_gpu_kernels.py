@@ -190,3 +190,37 @@ def test_gemm_2cta_epilogues():
     x = x0.clone()
     op_gemm(a, w, epi=2, bn=512, out=x)
     assert (x - (x0 + a.float() @ w.float().T)).abs().max() < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K,cluster", [(64, 2048, 2048, 4), (64, 2048, 8192, 4), (64, 2048, 2048, 0), (33, 256, 512, 2),
+                                           (7, 512, 256, 1), (64, 3072, 3072, 3), (1, 256, 256, 4), (32, 2048, 2048, 2)])
+def test_gemm_cluster_splitk_resid_norm(M, N, K, cluster):
+    """Decode-step GEMM (gemm_sk_tcgen05.cuh): the K range split over the CTAs of a thread-block cluster, partial tiles
+    reduced through distributed shared memory, epilogue = residual add + first half of the following RMSNorm:
+    x += a.W^T (fp32), a' = bf16(x * gamma), ss = per-32-column sums of x^2."""
+    from gpu_util import L, stream
+    from llm_np_cp_b200 import _lib
+    a = bf16_randn(M, K, std=1.0, seed=1)
+    w = bf16_randn(N, K, std=0.05, seed=2)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(M, N, generator=g).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV)
+    x = x0.clone()
+    a_out = torch.zeros((M, N), dtype=torch.bfloat16, device=DEV)
+    ss = torch.full((M, N // 32), -1.0, dtype=torch.float32, device=DEV)
+    _lib.check(L().b2_op_gemm_sk(a.data_ptr(), w.data_ptr(), x.data_ptr(), a_out.data_ptr(), gamma.data_ptr(), ss.data_ptr(),
+                                 M, N, K, cluster, stream()))
+    torch.cuda.synchronize()
+    ref = x0.double() + a.double() @ w.double().T
+    tol = 2e-5 * math.sqrt(K) * float(ref.abs().max()) + 1e-5           # fp32 accumulation-order differences only
+    assert (x.double() - ref).abs().max() <= tol, err_stats(x, ref.float())
+    want_a = (x * gamma).to(torch.bfloat16)                              # from the kernel's own fp32 x: exact rounding expected
+    assert (a_out.float() - want_a.float()).abs().max() <= want_a.float().abs().max() * 2 ** -7
+    want_ss = x.double().pow(2).view(M, N // 32, 32).sum(-1)
+    assert (ss.double() - want_ss).abs().max() <= 1e-5 * float(want_ss.max()) + 1e-6
+    # determinism: the reduction order inside the cluster is fixed
+    x2 = x0.clone()
+    _lib.check(L().b2_op_gemm_sk(a.data_ptr(), w.data_ptr(), x2.data_ptr(), a_out.data_ptr(), gamma.data_ptr(), ss.data_ptr(),
+                                 M, N, K, cluster, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(x, x2)
