@@ -739,6 +739,282 @@ attn_prefill_co_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant of the co-resident kernel: grid = 2 CTAs per SM, each CTA walks a static, heaviest-first list of
+// (q tile, head, batch) work items -- item t, t + grid, t + 2 grid, ... with items ordered by their kv length (longest
+// first, LPT) and the q heads of one kv head adjacent (their K/V tiles hit in L2).
+// What it removes: the fixed cost per 128-row tile of the one-tile-per-CTA kernel (measured 5.4 us of prologue -- launch,
+// barrier init, TMEM alloc, Q + first K load, first S -- and epilogue against ~1.9 us per kv iteration): barriers and
+// TMEM live for the whole kernel, the producer runs ahead across items (the next item's Q is requested as soon as the
+// last S = Q.K^T of the current one has retired, its K tiles as the ring slots free up), the MMA thread issues the next
+// item's first S while the softmax warps are still in the last kv tile / epilogue of the current one, and the epilogue
+// hands O back (o_free) after its TMEM loads, before the global stores.  All barrier parities come from running
+// counters (items, kv iterations, K / V tiles) that the three roles advance in lock step.
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(ATT_CO_THREADS, 2)
+attn_prefill_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                            const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, const int total_items) {
+  using Cfg = AttnCoCfg<HD>;
+  constexpr int BNKV = Cfg::BNKV;
+  constexpr int HB = HD / 64;
+  constexpr int SCH = BNKV / 32;
+  constexpr int OCH = HD / 32;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;                      // [2]
+  uint8_t* sV = sK + Cfg::K_STAGES * Cfg::KV_BYTES;     // [1]
+  uint8_t* sP = sV + Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;      // every S = Q.K^T of the item has retired: sQ may be overwritten
+  uint64_t* k_full = bars + 2;       // [2]
+  uint64_t* k_empty = bars + 4;      // [2]
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 8;       // S written by the tensor core
+  uint64_t* s_free = bars + 9;       // S copied to registers by all 128 softmax threads
+  uint64_t* p_ready = bars + 10;     // P written to smem by all 128 softmax threads
+  uint64_t* o_done = bars + 11;      // O += P.V finished
+  uint64_t* o_free = bars + 12;      // the epilogue has read O out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < Cfg::K_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_ready, 128);
+    mbar_init(o_done, 1);
+    mbar_init(o_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                               // Q/K/V and the cache length come from the preceding kernels
+  const int t0 = *p.t0_ptr;
+  const int T = t0 + p.S;
+  const int n_qt = (p.S + ATT_BM - 1) / ATT_BM;
+  const int BH = p.B * p.NH;
+  const uint32_t tS = tmem_base;            // S accumulator columns [0, BNKV)
+  const uint32_t tO = tmem_base + BNKV;     // O accumulator columns [BNKV, BNKV + HD)
+
+  // work item -> (q tile, head, batch) and its kv tile range; items are ordered heaviest (latest q tile) first
+  struct Item { int q0, h, b, jt0, n; };
+  auto item = [&](int t) {
+    Item w;
+    const int qt = n_qt - 1 - t / BH, bh = t - (t / BH) * BH;
+    w.h = bh % p.NH;
+    w.b = bh / p.NH;
+    w.q0 = qt * ATT_BM;
+    int kv_end = T;
+    if (p.causal) kv_end = min(T, t0 + w.q0 + ATT_BM);
+    int kv_begin = 0;
+    if (p.window > 0) kv_begin = max(0, t0 + w.q0 - p.window + 1);
+    w.jt0 = kv_begin / BNKV;
+    w.n = (kv_end + BNKV - 1) / BNKV - w.jt0;
+    return w;
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+
+  if (warp >= 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 4) {
+      // ------------------------------ TMA producer ------------------------------
+      if (elect_one()) {
+        uint32_t kc = 0, vc = 0, ic = 0;        // K tiles, V tiles, items loaded so far
+        for (int t = first; t < total_items; t += stride, ++ic) {
+          const Item w = item(t);
+          const int kvh = w.h / (p.NH / p.NKV);
+          mbar_wait(q_empty, (ic & 1) ^ 1);     // previous item's S products are done with sQ (fresh barrier: passes)
+          mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+            tma_load_2d(sQ + hb * (ATT_BM * 128), &tmap_q, q_full, w.h * HD + hb * 64, w.b * p.S + w.q0, kEvictFirst);
+          const int kv_row0 = (w.b * p.NKV + kvh) * p.Tmax;
+          auto load_k = [&](int it) {
+            const int st = kc & 1;
+            mbar_wait(&k_empty[st], ((kc >> 1) & 1) ^ 1);
+            mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
+#pragma unroll
+            for (int hb = 0; hb < HB; ++hb)
+              tma_load_2d(sK + st * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[st], hb * 64,
+                          kv_row0 + (w.jt0 + it) * BNKV, kEvictLast);
+            ++kc;
+          };
+          auto load_v = [&](int it) {
+            mbar_wait(v_empty, (vc & 1) ^ 1);
+            mbar_expect_tx(v_full, Cfg::KV_BYTES);
+#pragma unroll
+            for (int hb = 0; hb < HB; ++hb)
+              tma_load_2d(sV + hb * (BNKV * 128), &tmap_v, v_full, hb * 64, kv_row0 + (w.jt0 + it) * BNKV, kEvictLast);
+            ++vc;
+          };
+          if (w.n > 0) load_k(0);
+          if (w.n > 1) load_k(1);
+          if (w.n > 0) load_v(0);
+          for (int it = 0; it < w.n; ++it) {
+            if (it + 2 < w.n) load_k(it + 2);   // slot freed by S(it)
+            if (it + 1 < w.n) load_v(it + 1);   // slot freed by P.V(it)
+          }
+        }
+      }
+    } else if (warp == 5) {
+      // ------------------------------ MMA issuer ------------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, BNKV, 0, 0);   // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // P (K-major) x V (MN-major)
+        uint32_t kc = 0, vc = 0, gi = 0, ic = 0;   // K tiles consumed, V tiles consumed, kv iterations, items
+        auto issue_s = [&](bool last_of_item) {    // S = Q . K(kc)^T -> TMEM; k_full of the slot must be complete
+          const int st = kc & 1;
+          mbar_wait(&k_full[st], (kc >> 1) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sK + st * Cfg::KV_BYTES);
+#pragma unroll
+          for (int hb = 0; hb < HB; ++hb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tS, umma_smem_desc(smem_u32(sQ) + hb * (ATT_BM * 128) + k * 32, 16, 1024),
+                           umma_smem_desc(k_addr + hb * (BNKV * 128) + k * 32, 16, 1024), idesc_s, (hb | k) != 0 ? 1u : 0u);
+          umma_commit(&k_empty[st]);
+          if (last_of_item) umma_commit(q_empty);
+          umma_commit(s_full);
+          ++kc;
+        };
+        bool s0_issued = false;                    // the current item's S(0) was issued ahead, during the previous item
+        for (int t = first; t < total_items; t += stride, ++ic) {
+          const Item w = item(t);                  // w.n >= 1 always: the diagonal kv tile exists for every q tile
+          const int tn = t + stride;
+          const bool has_next = tn < total_items;
+          if (!s0_issued) {
+            mbar_wait(q_full, ic & 1);
+            issue_s(w.n == 1);
+          }
+          s0_issued = false;
+          for (int it = 0; it < w.n; ++it) {
+            const bool last = it + 1 == w.n;
+            if (!last) {
+              mbar_wait(s_free, gi & 1);           // S(it) is in registers
+              issue_s(it + 2 == w.n);
+            }
+            if (last && has_next) {
+              // overlap: while the softmax warps work on the last kv tile, issue the next item's S(0) as soon as S is
+              // free and its Q / K tiles have landed -- but never delay this item's last P.V for them
+              for (;;) {
+                if (!s0_issued && mbar_test_wait(s_free, gi & 1) && mbar_test_wait(q_full, (ic + 1) & 1) &&
+                    mbar_test_wait(&k_full[kc & 1], (kc >> 1) & 1)) {
+                  issue_s(item(tn).n == 1);
+                  s0_issued = true;
+                }
+                if (mbar_test_wait(p_ready, gi & 1)) break;
+                __nanosleep(40);
+              }
+            } else {
+              mbar_wait(p_ready, gi & 1);
+            }
+            mbar_wait(v_full, vc & 1);
+            if (it == 0) mbar_wait(o_free, (ic & 1) ^ 1);   // previous item's epilogue has read O (fresh barrier: passes)
+            tc_fence_after();
+            const uint32_t v_addr = smem_u32(sV);
+#pragma unroll
+            for (int kk = 0; kk < BNKV / 16; ++kk)
+              umma_bf16_ss(tO, umma_smem_desc(smem_u32(sP) + (kk >> 2) * (ATT_BM * 128) + (kk & 3) * 32, 16, 1024),
+                           umma_smem_desc(v_addr + kk * (16 * 128), BNKV * 128, 1024), idesc_o, (it | kk) != 0 ? 1u : 0u);
+            umma_commit(v_empty);
+            umma_commit(o_done);
+            ++vc;
+            ++gi;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax / correction / epilogue ------------------------------
+    setmaxnreg_inc<216>();
+    const int r = warp * 32 + lane;                 // q row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = p.scale * LOG2E;
+    const bool cap = p.softcap > 0.f;
+    const float cap_in = cap ? p.scale / p.softcap : 0.f, cap_out = p.softcap * LOG2E;
+    uint32_t gi = 0;
+    for (int t = first; t < total_items; t += stride) {
+      const Item w = item(t);
+      const int qpos = t0 + w.q0 + r;
+      float m_used = -INFINITY, l = 0.f;
+      for (int it = 0; it < w.n; ++it) {
+        const int kv0 = (w.jt0 + it) * BNKV;
+        const bool need_mask = (p.causal && kv0 + BNKV - 1 > t0 + w.q0) || (kv0 + BNKV > T) ||
+                               (p.window > 0 && kv0 < t0 + w.q0 + ATT_BM - p.window);
+        int lo = 0, hi = BNKV;
+        if (need_mask) {
+          int last = T - 1;
+          if (p.causal) last = min(last, qpos);
+          hi = min(BNKV, last - kv0 + 1);
+          if (p.window > 0) lo = max(0, qpos - p.window + 1 - kv0);
+        }
+        const unsigned span = hi > lo ? static_cast<unsigned>(hi - lo) : 0u;
+        mbar_wait(s_full, gi & 1);
+        tc_fence_after();
+        att_softmax_tile<SCH, OCH>(tS + lane_off, tO + lane_off, sP, r, need_mask, lo, span, cap, sl2, cap_in, cap_out, m_used, l,
+                                   it > 0, o_done, (gi - 1) & 1, s_free);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+        ++gi;
+      }
+      // epilogue: O (TMEM) -> registers, hand O back to the tensor core, then scale / convert / store
+      mbar_wait(o_done, (gi - 1) & 1);
+      tc_fence_after();
+      uint32_t o[OCH][32];
+#pragma unroll
+      for (int c = 0; c < OCH; ++c) tmem_ld32(tO + lane_off + c * 32, o[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);
+      if (w.q0 + r < p.S) {
+        const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+        __nv_bfloat16* orow = p.out + static_cast<size_t>(w.b * p.S + w.q0 + r) * p.ldo + w.h * HD;
+#pragma unroll
+        for (int c = 0; c < OCH; ++c) {
+          uint4* d = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(o[c][8 * i + 0]) * inv_l, __uint_as_float(o[c][8 * i + 1]) * inv_l);
+            u.y = pack_bf16(__uint_as_float(o[c][8 * i + 2]) * inv_l, __uint_as_float(o[c][8 * i + 3]) * inv_l);
+            u.z = pack_bf16(__uint_as_float(o[c][8 * i + 4]) * inv_l, __uint_as_float(o[c][8 * i + 5]) * inv_l);
+            u.w = pack_bf16(__uint_as_float(o[c][8 * i + 6]) * inv_l, __uint_as_float(o[c][8 * i + 7]) * inv_l);
+            d[i] = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Decode attention (q_len == 1): bandwidth/latency-bound, CUDA cores.  One warp per (batch, q head).
 // A kv position is owned by LPP = HD/16 adjacent lanes (16 head-dim elements = two 16-byte loads each), so
 // 32/LPP positions are in flight per warp iteration and a K/V row is read as one contiguous 128..512-byte

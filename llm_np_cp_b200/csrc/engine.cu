@@ -338,6 +338,7 @@ static int launch_gemm(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
   if (p.split_k < 1 || (p.K / GEMM_BK) % p.split_k != 0)
     return fail(B2_ERR_ARG, "split_k=%d must divide K/64=%d", p.split_k, p.K / GEMM_BK);
   if (p.split_k > 1 && epi != EPI_RESID && epi != EPI_F32) return fail(B2_ERR_ARG, "split_k needs the residual or fp32 epilogue");
+  if (p.ss_in && p.M > GEMM_BM) return fail(B2_ERR_ARG, "the split-RMSNorm row scale is a few-row (M <= 128) feature");
   if ((epi == EPI_F32 || epi == EPI_RESID) && p.ldo % 4 != 0) return fail(B2_ERR_ARG, "fp32 output stride %d must be a multiple of 4", p.ldo);
 #define GEMM_CASE(BN_, EPI_) \
   if (bn == BN_ && epi == EPI_) return launch_gemm_t<BN_, EPI_>(ta, tb, tc, p, st)
@@ -384,6 +385,18 @@ static int launch_attn_co_t(const CUtensorMap& tq, const CUtensorMap& tk, const 
   return B2_OK;
 }
 
+template <int HD>
+static int launch_attn_persist_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                                 cudaStream_t st) {
+  auto kern = attn_prefill_persist_kernel<HD>;
+  static std::atomic<uint64_t> attr{0};
+  CKR(smem_attr_once(kern, AttnCoCfg<HD>::SMEM_BYTES, attr, true));
+  const int items = ((p.S + ATT_BM - 1) / ATT_BM) * p.NH * p.B;
+  const int slots = 2 * num_sms();                  // two co-resident CTAs per SM
+  CK(launch_k(kern, dim3(items < slots ? items : slots), dim3(ATT_CO_THREADS), AttnCoCfg<HD>::SMEM_BYTES, st, tq, tk, tv, p, items));
+  return B2_OK;
+}
+
 // prefill attention dispatch: the co-resident kernel (one q tile per CTA, two CTAs per SM) for head_dim 64/128 unless
 // B2_ATTN_SINGLE is set or the sequence fits one q tile; the one-CTA-per-SM single-tile kernel otherwise (head_dim 256:
 // TMEM/smem budget; precise mode: three MMAs per product).
@@ -411,6 +424,8 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
     if (HD == 128) return launch_attn_t<128, 2>(tq, tk, tv, p, st);
     return fail(B2_ERR_ARG, "precise mode supports head_dim 64 and 128 only");
   }
+  static const bool one_tile_ctas = getenv("B2_ATTN_CO_ONESHOT") != nullptr;   // A/B: the one-tile-per-CTA kernel of round 1
+  if (co && !one_tile_ctas) return HD == 64 ? launch_attn_persist_t<64>(tq, tk, tv, p, st) : launch_attn_persist_t<128>(tq, tk, tv, p, st);
   if (co) return HD == 64 ? launch_attn_co_t<64>(tq, tk, tv, p, st) : launch_attn_co_t<128>(tq, tk, tv, p, st);
   if (HD == 64) return launch_attn_t<64, 1>(tq, tk, tv, p, st);
   if (HD == 128) return launch_attn_t<128, 1>(tq, tk, tv, p, st);

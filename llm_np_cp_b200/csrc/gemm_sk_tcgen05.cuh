@@ -84,8 +84,10 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   pdl_trigger();
   tc_fence_before();
-  if (CK > 1) cluster_sync_all();        // every CTA of the cluster is running: its shared memory may be written remotely
-  else __syncthreads();
+  // Cluster barrier #0 ("every CTA of the cluster is running, its shared memory may be written remotely") is split:
+  // arrive here, wait only right before the first remote store -- the weight stream starts without it.
+  if (CK > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -144,54 +146,92 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
   const bool epi_warp = warp >= 2 && quarter * 32 < a_rows;
   const int row_in_tile = quarter * 32 + lane;
+  const int row = mb * GEMM_BM + row_in_tile;
+  const bool row_ok = row < p.M;
   const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  const int col = nb * BN + half * 32;                       // this warp's 32 columns of the tile
+  uint32_t r[32];                                            // this thread's 32 accumulators (row = lane of the quarter)
+  float4 xv[8];                                              // EPI_RESID_NORM: the residual stream values they are added to
+  float rs_row = 1.0f;                                       // EPI_QKV_ROPE: 1/rms of the row (split RMSNorm)
   if (epi_warp) {
+    if (rank == 0) {   // everything the epilogue needs from earlier kernels is fetched while the weights stream
+      pdl_wait();
+      if (EPI == EPI_RESID_NORM && row_ok) {
+        const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = __ldcg(xr + j);
+      }
+      if (EPI == EPI_QKV_ROPE && p.ss_in && row_ok) rs_row = row_rs(p, row);
+    }
     mbar_wait(tfull, 0);
     tc_fence_after();
-    if (rank != 0) {   // ship this CTA's partial tile to rank 0: chunk `half` (32 columns) of this warp's 32 rows
-      uint32_t r[32];
-      tmem_ld32(trow + half * 32, r);
-      tmem_ld_wait();
+    tmem_ld32(trow + half * 32, r);
+    tmem_ld_wait();
+  }
+  if (CK > 1) {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // barrier #0: the peers are running
+    if (epi_warp && rank != 0) {   // ship this CTA's partial tile to rank 0: 32 columns of this thread's row
       const uint32_t base = mapa_u32(smem_u32(sRed), 0) + (rank - 1) * (SK_MAX_ROWS * BN * 4) + row_in_tile * (BN * 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int chunk = half * 8 + j;                                   // 16-byte chunk inside the 256-byte row
+        const int chunk = half * 8 + j;                                     // 16-byte chunk inside the 256-byte row
         st_cluster_f4(base + ((chunk ^ (row_in_tile & 15)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
       }
     }
-  }
-  if (CK > 1) {
     tc_fence_before();
-    cluster_sync_all();                  // release/acquire at cluster scope: the partial tiles are in rank 0's shared memory
+    cluster_sync_all();                  // barrier #1 (release / acquire at cluster scope): the partial tiles are in rank 0's smem
     tc_fence_after();
   }
   if (epi_warp && rank == 0) {
-    if (CK > 1) {   // accumulate the peers' tiles (rank order: deterministic) back into TMEM, then the ordinary epilogue
-      uint32_t r[32];
-      tmem_ld32(trow + half * 32, r);
-      tmem_ld_wait();
-      for (int pr = 0; pr < CK - 1; ++pr) {
-        const uint8_t* src = sRed + pr * (SK_MAX_ROWS * BN * 4) + row_in_tile * (BN * 4);
+    for (int pr = 0; pr < CK - 1; ++pr) {   // add the peers' tiles in rank order: deterministic
+      const uint8_t* src = sRed + pr * (SK_MAX_ROWS * BN * 4) + row_in_tile * (BN * 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int chunk = half * 8 + j;
+        const float4 v = *reinterpret_cast<const float4*>(src + ((chunk ^ (row_in_tile & 15)) << 4));
+        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+      }
+    }
+    if constexpr (EPI == EPI_RESID_NORM) {
+      // x += acc; a' = bf16(x * gamma_next); ss[row][32-column block] = sum x^2  (same arithmetic as gemm_epilogue's branch)
+      if (row_ok) {
+        float4* xw = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
+        const float4* g4 = reinterpret_cast<const float4*>(p.gamma_next + col);
+        float v[32], ss = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int chunk = half * 8 + j;
-          const float4 v = *reinterpret_cast<const float4*>(src + ((chunk ^ (row_in_tile & 15)) << 4));
-          r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
-          r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
-          r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
-          r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+          float4 x4 = xv[j];
+          x4.x += __uint_as_float(r[4 * j]);
+          x4.y += __uint_as_float(r[4 * j + 1]);
+          x4.z += __uint_as_float(r[4 * j + 2]);
+          x4.w += __uint_as_float(r[4 * j + 3]);
+          xw[j] = x4;
+          ss += (x4.x * x4.x + x4.y * x4.y) + (x4.z * x4.z + x4.w * x4.w);
+          const float4 gg = __ldg(g4 + j);
+          v[4 * j] = x4.x * gg.x;
+          v[4 * j + 1] = x4.y * gg.y;
+          v[4 * j + 2] = x4.z * gg.z;
+          v[4 * j + 3] = x4.w * gg.w;
         }
+        store_bf16x32(p.a_out + static_cast<size_t>(row) * p.N + col, v);
+        p.ss_out[static_cast<size_t>(row) * (p.N / 32) + (col >> 5)] = ss;
       }
-      tmem_st32(trow + half * 32, r);
-      tmem_st_wait();
+    } else {
+      // QKV: the RoPE epilogue pairs the two 32-column chunks of a head (x1 | x2) that the two warps of this quarter hold:
+      // put the finished sums back into TMEM and run the ordinary epilogue
+      if (CK > 1) {
+        tmem_st32(trow + half * 32, r);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      named_bar_sync(1 + quarter, 64);
+      tc_fence_after();
+      gemm_epilogue<BN, EPI>(p, &tmap_c, nullptr, tmem_base, mb, nb, 0, quarter, half, lane, rs_row);
     }
-    // the QKV epilogue pairs 32-column chunks across the two warps of a quarter (x1 / x2 halves of a head)
-    tc_fence_before();
-    named_bar_sync(1 + quarter, 64);
-    tc_fence_after();
-    pdl_wait();                          // RoPE tables / residual stream / ss come from earlier kernels
-    gemm_epilogue<BN, EPI>(p, &tmap_c, nullptr, tmem_base, mb, nb, 0, quarter, half, lane);
   }
   tc_fence_before();
   __syncthreads();

@@ -69,13 +69,20 @@ struct GemmParams {
 
 // 1/sqrt(mean(x^2) + eps) of a row whose partial sums of squares were left by an EPI_RESID_NORM producer (or by
 // embed_norm_row_kernel); fixed summation order => deterministic and independent of the batch neighbours
+// All loads are issued before the first add (one L2 round trip instead of ss_n / 4 dependent ones): the callers run
+// this once per kernel, while the main loop of their first tile is still streaming weights.
+constexpr int SS_MAX4 = 24;   // float4 per row: hidden_size <= 3072
 __device__ __forceinline__ float row_rs(const GemmParams& p, int row) {
-  const float* s = p.ss_in + static_cast<size_t>(row) * p.ss_n;
+  const float4* s = reinterpret_cast<const float4*>(p.ss_in + static_cast<size_t>(row) * p.ss_n);
+  const int n4 = p.ss_n >> 2;
+  float4 v[SS_MAX4];
+#pragma unroll
+  for (int i = 0; i < SS_MAX4; ++i)
+    if (i < n4) v[i] = __ldcg(s + i);
   float t = 0.f;
-  for (int i = 0; i < p.ss_n; i += 4) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(s + i));
-    t += (v.x + v.y) + (v.z + v.w);
-  }
+#pragma unroll
+  for (int i = 0; i < SS_MAX4; ++i)
+    if (i < n4) t += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   return 1.0f / sqrtf(t / static_cast<float>(p.norm_dim) + p.norm_eps);
 }
 
@@ -122,8 +129,11 @@ __device__ __forceinline__ void split_lo(const float (&v)[32], float (&lo)[32]) 
 // Epilogue of one tile for one warp.  `quarter` = TMEM lane quarter (rows), `half` = which of the two
 // warps sharing that quarter (takes column groups of its parity), `slab` = this warp's 4 KB staging.
 template <int BN, int EPI>
+// `rs_in`: 1/rms of this thread's row when the A operand came out of a split RMSNorm (p.ss_in != nullptr), computed once
+// per kernel by the caller (row_rs); ignored otherwise.
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtensorMap* tmap_c, uint8_t* slab,
-                                              uint32_t tacc, int mb, int nb, int ks, int quarter, int half, int lane) {
+                                              uint32_t tacc, int mb, int nb, int ks, int quarter, int half, int lane,
+                                              float rs_in = 1.0f) {
   const int row0 = mb * GEMM_BM + quarter * 32;
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
@@ -133,7 +143,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
   if constexpr (EPI == EPI_F32 || EPI == EPI_RESID) {
     // registers -> swizzled smem slab (row = lane, 16-byte chunk j at j ^ (lane & 7)) -> TMA store / reduce-add
     const float inv_cap = p.softcap > 0.f ? 1.0f / p.softcap : 0.f;
-    const float rs = (EPI == EPI_F32 && p.ss_in && row_ok) ? row_rs(p, row) : 1.0f;
+    const float rs = (EPI == EPI_F32 && p.ss_in) ? rs_in : 1.0f;
 #pragma unroll 1
     for (int c = half; c < BN / 32; c += 2) {
       const int col = col0 + c * 32;
@@ -187,7 +197,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
   } else if constexpr (EPI == EPI_GLU) {
     // W rows are interleaved in 32-row groups: [gate 32j..32j+31 | up 32j..32j+31] -> column chunk 2j is
     // gate, chunk 2j+1 is up, output column = N/2-space (col0/2 + 32j).
-    const float rs = (p.ss_in && row_ok) ? row_rs(p, row) : 1.0f;
+    const float rs = p.ss_in ? rs_in : 1.0f;
 #pragma unroll 1
     for (int j = half; j < BN / 64; j += 2) {
       const int col = col0 + j * 64;
@@ -260,7 +270,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
     int tab_i = -1;
     // row scale of a split RMSNorm (decode step only: few-row tiles; the 256-wide prefill instantiations skip it)
     constexpr bool SCALE = BN <= 128;
-    const float rs = (SCALE && p.ss_in && row_ok) ? row_rs(p, row) : 1.0f;
+    const float rs = (SCALE && p.ss_in) ? rs_in : 1.0f;
 #pragma unroll 1
     for (int t = half; t < BN / 64; t += 2) {
       const int hh = t / half_chunks, i = t - hh * half_chunks;
@@ -485,12 +495,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* slab = sStage + ew * 4096;
     uint32_t acc = 0, acc_phase = 0;
     pdl_wait();                                // residual / tables are read and outputs written only after this
+    // split RMSNorm (decode step, one m-block): this thread's row scale, fetched while the first tile's weights stream
+    float rs_row = 1.0f;
+    if (p.ss_in && quarter * 32 + lane < p.M) rs_row = row_rs(p, quarter * 32 + lane);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int mb, nb, kb0;
       tile_coords(tile, mb, nb, kb0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      gemm_epilogue<BN, EPI>(p, &tmap_c, slab, tmem_base + acc * BN, mb, nb, kb0 / KB, quarter, half, lane);
+      gemm_epilogue<BN, EPI>(p, &tmap_c, slab, tmem_base + acc * BN, mb, nb, kb0 / KB, quarter, half, lane, rs_row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
