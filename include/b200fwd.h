@@ -51,7 +51,7 @@ typedef struct b2_config {
   int32_t always_causal;        /* 0 = reference quirk: no mask when q_len <= 2 (llama3.2_model_numpy.py:479) */
   int32_t precise;              /* 1: parity mode -- every bf16 activation is carried as hi+lo bf16 planes (exact weights,
                                    2x-K weight GEMMs, 3 MMAs per attention product): logits within 1e-2 of the
-                                   reference at ~3x the cost; head_dim 64/128 only */
+                                   reference at ~2-3x the cost */
   /* HF "llama3" RoPE frequency scaling (transformers modeling_rope_utils._compute_llama3_parameters); the reference
    * never applies it (llama3.2_model_numpy.py:47 uses plain base^(-2i/HD)).  rope_factor <= 1 = off (reference). */
   float rope_factor;                    /* Llama-3.2: 32 */

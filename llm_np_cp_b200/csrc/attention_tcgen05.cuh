@@ -71,13 +71,17 @@ constexpr int ATT_THREADS = 192;
 // hi.hi + hi.lo + lo.hi)
 template <int HD, int NP = 1>
 struct AttnCfg {
-  static constexpr int BNKV = (NP == 2) ? 64 : ((HD <= 128) ? 128 : 64);
-  static constexpr int KV_STAGES = 2;
+  // precise mode at head_dim 256 (Gemma-2): Q hi+lo alone is 128 KB, so kv tiles are 32 wide and K / V single-buffered
+  static constexpr int BNKV = (NP == 2) ? (HD <= 128 ? 64 : 32) : ((HD <= 128) ? 128 : 64);
+  static constexpr int KV_STAGES = (NP == 2 && HD > 128) ? 1 : 2;
   static constexpr int Q_BYTES = NP * ATT_BM * HD * 2;
   static constexpr int KV_BYTES = NP * BNKV * HD * 2;  // one K or V tile (all planes)
-  static constexpr int P_BYTES = NP * ATT_BM * BNKV * 2;
+  static constexpr int P_PLANE = ATT_BM * 128 * ((BNKV + 63) / 64);   // P rows are 128-byte swizzled rows (64 columns) even when
+                                                                      // only 32 of them are used
+  static constexpr int P_BYTES = NP * P_PLANE;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + P_BYTES + BAR_BYTES + 768;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static constexpr int TMEM_USED = BNKV + HD;
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
 };
@@ -292,7 +296,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   using Cfg = AttnCfg<HD, NP>;
   constexpr int QP = ATT_BM * HD * 2;                  // bytes of one Q plane
   constexpr int KP = Cfg::BNKV * HD * 2;               // bytes of one K / V plane of a stage
-  constexpr int PP = ATT_BM * Cfg::BNKV * 2;           // bytes of one P plane
+  constexpr int PP = Cfg::P_PLANE;                     // bytes of one P plane
   constexpr int BNKV = Cfg::BNKV;
   constexpr int HB = HD / 64;        // 64-column (128-byte) blocks per head
   constexpr int SCH = BNKV / 32;     // 32-column chunks of S per row

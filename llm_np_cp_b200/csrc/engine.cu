@@ -415,14 +415,15 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
   const bool co = !precise && !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
   const int planes = precise ? 2 : 1;
   const uint64_t kv_rows = static_cast<uint64_t>(planes) * (precise ? p.kv_lo_row : static_cast<uint64_t>(p.B) * p.NKV * p.Tmax);
-  const int bnkv = precise ? 64 : (co ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64));
+  const int bnkv = precise ? (HD <= 128 ? 64 : 32) : (co ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64));
   CKR(make_tmap(&tq, q, static_cast<uint64_t>(p.B) * p.S, static_cast<uint64_t>(planes) * p.NH * HD, ldq, ATT_BM));
   CKR(make_tmap(&tk, kc, kv_rows, HD, HD, bnkv));
   CKR(make_tmap(&tv, vc, kv_rows, HD, HD, bnkv));
   if (precise) {
     if (HD == 64) return launch_attn_t<64, 2>(tq, tk, tv, p, st);
     if (HD == 128) return launch_attn_t<128, 2>(tq, tk, tv, p, st);
-    return fail(B2_ERR_ARG, "precise mode supports head_dim 64 and 128 only");
+    if (HD == 256) return launch_attn_t<256, 2>(tq, tk, tv, p, st);
+    return fail(B2_ERR_ARG, "head_dim %d unsupported (64/128/256)", HD);
   }
   static const bool one_tile_ctas = getenv("B2_ATTN_CO_ONESHOT") != nullptr;   // A/B: the one-tile-per-CTA kernel of round 1
   if (co && !one_tile_ctas) return HD == 64 ? launch_attn_persist_t<64>(tq, tk, tv, p, st) : launch_attn_persist_t<128>(tq, tk, tv, p, st);
@@ -775,7 +776,6 @@ extern "C" int b2_engine_create(const b2_config* cfg, int device, b2_engine** ou
   if (c.intermediate_size % 64) return fail(B2_ERR_ARG, "intermediate_size %d must be a multiple of 64", c.intermediate_size);
   if (c.vocab_size % 32) return fail(B2_ERR_ARG, "vocab_size %d must be a multiple of 32", c.vocab_size);
   if (c.max_positions <= 0) return fail(B2_ERR_ARG, "max_positions must be positive");
-  if (c.precise && c.head_dim == 256) return fail(B2_ERR_ARG, "precise (hi/lo split) mode supports head_dim 64 and 128 only");
   const int tpw = c.tp_world > 1 ? c.tp_world : 1;
   if (tpw > 1) {
     if (c.tp_rank < 0 || c.tp_rank >= tpw) return fail(B2_ERR_ARG, "tp_rank %d outside [0, %d)", c.tp_rank, tpw);

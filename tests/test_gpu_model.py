@@ -308,7 +308,8 @@ def test_forward_host_and_sampling():
 PRECISE_TOL = 1e-2
 
 
-@pytest.mark.parametrize("name", ["llama_tiny_prefill", "llama_tiny128_prefill", "llama_tiny_long", "llama_tiny_qlen2"])
+@pytest.mark.parametrize("name", ["llama_tiny_prefill", "llama_tiny128_prefill", "llama_tiny_long", "llama_tiny_qlen2",
+                                  "gemma2_tiny_prefill"])      # head_dim 64 / 128 / 256 (Gemma-2: 32-wide kv tiles)
 def test_precise_prefill_within_1e2_of_reference(name):
     meta, arr = load_golden(name)
     cfg, w, model = build(meta, precise=True)
@@ -320,8 +321,9 @@ def test_precise_prefill_within_1e2_of_reference(name):
         assert np.abs(h.cpu().numpy() - arr["hidden"][i]).max() <= PRECISE_TOL
 
 
-def test_precise_decode_within_1e2_of_reference():
-    meta, arr = load_golden("llama_tiny_decode")
+@pytest.mark.parametrize("name", ["llama_tiny_decode", "gemma2_tiny_decode"])
+def test_precise_decode_within_1e2_of_reference(name):
+    meta, arr = load_golden(name)
     cfg, w, model = build(meta, precise=True)
     S, dec = meta["S"], meta["decode_steps"]
     cache = M.KVCache(max_tokens=64)
