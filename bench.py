@@ -195,8 +195,9 @@ def measure_decode(cfg, model, dev, dist, rank, world, local, pk, B, P, NT, step
     out_tp = None
     if tp > 1:
         H = cfg.hidden_size
-        out_tp = {"world": tp, "nccl_calls_per_token_step": stt["comm_calls"] / (steps * NT),
-                  "payload_bytes_per_token_step": stt["comm_bytes"] / (steps * NT),
+        Lc = cfg.num_hidden_layers      # the graph-replayed steps do not pass through the host-side counters: static count
+        out_tp = {"world": tp, "nccl_calls_per_token_step": 2 * Lc + 1,
+                  "payload_bytes_per_token_step": 2 * Lc * B * H * 4 + B * cfg.vocab_size * 4,
                   "algorithmic_nvlink_bytes_per_allreduce": 2.0 * B * H * 4 * (tp - 1) / tp,
                   "note": "2 all-reduces of [B,H] fp32 partial sums per layer (after o_proj and down_proj) + 1 all-gather of logits"}
     return {
@@ -356,7 +357,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        step_resident()        # one extra untimed step so nvidia-smi is sampling under load before t0
+    step_resident()            # one extra untimed step (every rank: a tensor-parallel step contains collectives) so that
+                               # nvidia-smi is sampling under load before t0
     model.set_timing(max(1, a.event_every))   # restart the every-k-th counter; first timed step carries events
     model.reset_stats()        # only the timed steps below count towards the roofline figures
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -89,8 +89,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (leader) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));   // both CTAs' bytes
           const int ka = kb * GEMM_BK;
           const int kw = ka >= p.k_wrap ? ka - p.k_wrap : ka;
-          tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmap_a, full_leader, ka, mb * 2 * GEMM_BM + rank * GEMM_BM);
-          tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmap_b, full_leader, kw, nb * BN + rank * (BN / 2));
+          tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmap_a, full_leader, ka, mb * 2 * GEMM_BM + rank * GEMM_BM,
+                          p.stream_out ? kEvictLast : kEvictNormal);
+          tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmap_b, full_leader, kw, nb * BN + rank * (BN / 2),
+                          p.stream_out ? kEvictFirst : kEvictNormal);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;

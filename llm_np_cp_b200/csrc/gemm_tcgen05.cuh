@@ -51,6 +51,8 @@ struct GemmParams {
   const float* rope_cos;   // [max_pos][HD/2]
   const float* rope_sin;
   int kv_lo_off;           // precise mode: element offset of the lo plane of the caches (0 = none)
+  int stream_out;          // EPI_F32 whose output is much larger than L2 (lm_head logits): A loads evict-last, W loads and C stores
+                           // evict-first, so the write-once C stream and the read-once W stream do not displace A
   int a_box_rows;          // 1-CTA kernel: rows of A one TMA box brings in (32/64 when M is that small, else 0 = 128);
                            // the remaining rows of the 128-row MMA tile are zeroed once instead of fetched every k-step
   // ---- RMSNorm split across two GEMMs (decode step; LlamaRMSNorm_np, llama3.2_model_numpy.py:256-278):
@@ -168,7 +170,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && row0 < p.M) {
-        if (EPI == EPI_F32) tma_store_2d(tmap_c, slab, col, ks * p.split_rows + row0);
+        if (EPI == EPI_F32) {
+          if (p.stream_out) tma_store_2d_hint(tmap_c, slab, col, ks * p.split_rows + row0, kEvictFirst);
+          else tma_store_2d(tmap_c, slab, col, ks * p.split_rows + row0);
+        }
         else tma_reduce_add_2d(tmap_c, slab, col, row0);   // x += acc  (fp32 residual stream)
         tma_store_commit();
       }
