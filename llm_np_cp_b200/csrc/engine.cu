@@ -700,11 +700,12 @@ static int eng_gemm(b2_engine* e, cudaStream_t st, int bn, int epi, const bf16* 
   tc = ta;
   if (epi == EPI_F32 || epi == EPI_RESID) CKR(get_tmap(e, p.out, c_rows ? c_rows : p.M, p.N, p.ldo, 32, &tc, true));
   p.band_m = pick_band(p.N, p.k_wrap);
-  // lm_head-like GEMM (fp32 output far larger than L2, W larger than L2): one band over all of M with A pinned in L2
-  // (evict-last), W and C streamed (evict-first) -- each W tile then comes from HBM once.  B2_LMHEAD_BANDS=1 keeps the
-  // banded rasterisation (A/B knob).
-  static const bool lm_bands = getenv("B2_LMHEAD_BANDS") != nullptr;
-  if (two_cta && epi == EPI_F32 && !lm_bands && 2.0 * p.N * p.k_wrap > 96e6 && 2.0 * p.M * p.K <= 80e6) {
+  // lm_head-like GEMM (fp32 output far larger than L2, W larger than L2), B2_LMHEAD_STREAM=1: one band over all of M with
+  // A pinned in L2 (evict-last), W and C streamed (evict-first) -- each W tile then comes from HBM once.  Measured on
+  // B200 (same-box A/B): 1-3 % SLOWER per step than the banded rasterisation (the kernel is not
+  // DRAM-bound and the single band gives up W-tile reuse inside L2 across concurrent clusters), so it stays opt-in.
+  static const bool lm_stream = getenv("B2_LMHEAD_STREAM") != nullptr;
+  if (two_cta && epi == EPI_F32 && lm_stream && 2.0 * p.N * p.k_wrap > 96e6 && 2.0 * p.M * p.K <= 80e6) {
     p.stream_out = 1;
     p.band_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   }
