@@ -25,6 +25,7 @@ namespace b2 {
 
 struct AttnParams {
   int B, S, NH, NKV, Tmax;
+  KvPages pages;         // block table of a paged cache (table == nullptr: dense [B][NKV][Tmax][HD] planes)
   const int* t0_ptr;     // tokens already cached before this call (device scalar)
   float scale;           // 1/sqrt(head_dim) (reference) or query_pre_attn_scalar^-0.5 (HF flag)
   float softcap;         // 0 = off
@@ -372,10 +373,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int hb = 0; hb < HB; ++hb)
           tma_load_2d(sQ + pl * QP + hb * (ATT_BM * 128), &tmap_q, bar_q, pl * p.q_lo_col + h * HD + hb * 64, b * p.S + q0,
                       kEvictFirst);
-      const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
       int stage = 0;
       uint32_t phase = 0;
       for (int j = jt0; j < jt1; ++j) {
+        const int trow = static_cast<int>(kv_row(p.pages, b, kvh, p.NKV, p.Tmax, j * BNKV));   // first row of kv tile j
         mbar_wait(&kv_empty[stage], phase ^ 1);
         mbar_expect_tx(&k_full[stage], Cfg::KV_BYTES);
 #pragma unroll
@@ -383,14 +384,14 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int hb = 0; hb < HB; ++hb)
             tma_load_2d(sK + stage * Cfg::KV_BYTES + pl * KP + hb * (BNKV * 128), &tmap_k, &k_full[stage], hb * 64,
-                        pl * p.kv_lo_row + kv_row0 + j * BNKV, kEvictLast);
+                        pl * p.kv_lo_row + trow, kEvictLast);
         mbar_expect_tx(&v_full[stage], Cfg::KV_BYTES);
 #pragma unroll
         for (int pl = 0; pl < NP; ++pl)
 #pragma unroll
           for (int hb = 0; hb < HB; ++hb)
             tma_load_2d(sV + stage * Cfg::KV_BYTES + pl * KP + hb * (BNKV * 128), &tmap_v, &v_full[stage], hb * 64,
-                        pl * p.kv_lo_row + kv_row0 + j * BNKV, kEvictLast);
+                        pl * p.kv_lo_row + trow, kEvictLast);
         if (++stage == Cfg::KV_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -610,22 +611,23 @@ attn_prefill_co_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 #pragma unroll
         for (int hb = 0; hb < HB; ++hb)
           tma_load_2d(sQ + hb * (ATT_BM * 128), &tmap_q, bar_q, h * HD + hb * 64, b * p.S + q0, kEvictFirst);
-        const int kv_row0 = (b * p.NKV + kvh) * p.Tmax;
+        auto tile_row = [&](int it) { return static_cast<int>(kv_row(p.pages, b, kvh, p.NKV, p.Tmax, (jt0 + it) * BNKV)); };
         auto load_k = [&](int it) {               // it = tile index relative to jt0
           const int st = it & 1;
+          const int trow = tile_row(it);
           mbar_wait(&k_empty[st], ((it >> 1) & 1) ^ 1);
           mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
 #pragma unroll
           for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(sK + st * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[st], hb * 64,
-                        kv_row0 + (jt0 + it) * BNKV, kEvictLast);
+            tma_load_2d(sK + st * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[st], hb * 64, trow, kEvictLast);
         };
         auto load_v = [&](int it) {
+          const int trow = tile_row(it);
           mbar_wait(v_empty, (it & 1) ^ 1);
           mbar_expect_tx(v_full, Cfg::KV_BYTES);
 #pragma unroll
           for (int hb = 0; hb < HB; ++hb)
-            tma_load_2d(sV + hb * (BNKV * 128), &tmap_v, v_full, hb * 64, kv_row0 + (jt0 + it) * BNKV, kEvictLast);
+            tma_load_2d(sV + hb * (BNKV * 128), &tmap_v, v_full, hb * 64, trow, kEvictLast);
         };
         if (n_tiles > 0) load_k(0);
         if (n_tiles > 1) load_k(1);
@@ -850,23 +852,24 @@ attn_prefill_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __
 #pragma unroll
           for (int hb = 0; hb < HB; ++hb)
             tma_load_2d(sQ + hb * (ATT_BM * 128), &tmap_q, q_full, w.h * HD + hb * 64, w.b * p.S + w.q0, kEvictFirst);
-          const int kv_row0 = (w.b * p.NKV + kvh) * p.Tmax;
+          auto tile_row = [&](int it) { return static_cast<int>(kv_row(p.pages, w.b, kvh, p.NKV, p.Tmax, (w.jt0 + it) * BNKV)); };
           auto load_k = [&](int it) {
             const int st = kc & 1;
+            const int trow = tile_row(it);          // (block-table lookup for a paged cache) before the slot wait
             mbar_wait(&k_empty[st], ((kc >> 1) & 1) ^ 1);
             mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
 #pragma unroll
             for (int hb = 0; hb < HB; ++hb)
-              tma_load_2d(sK + st * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[st], hb * 64,
-                          kv_row0 + (w.jt0 + it) * BNKV, kEvictLast);
+              tma_load_2d(sK + st * Cfg::KV_BYTES + hb * (BNKV * 128), &tmap_k, &k_full[st], hb * 64, trow, kEvictLast);
             ++kc;
           };
           auto load_v = [&](int it) {
+            const int trow = tile_row(it);
             mbar_wait(v_empty, (vc & 1) ^ 1);
             mbar_expect_tx(v_full, Cfg::KV_BYTES);
 #pragma unroll
             for (int hb = 0; hb < HB; ++hb)
-              tma_load_2d(sV + hb * (BNKV * 128), &tmap_v, v_full, hb * 64, kv_row0 + (w.jt0 + it) * BNKV, kEvictLast);
+              tma_load_2d(sV + hb * (BNKV * 128), &tmap_v, v_full, hb * 64, trow, kEvictLast);
             ++vc;
           };
           if (w.n > 0) load_k(0);
@@ -1030,7 +1033,8 @@ __global__ void __launch_bounds__(128)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kc,
                    const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int ldo, int B, int NH,
                    int NKV, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap, int window,
-                   int q_lo_col, size_t kv_lo_off, int out_lo_col) {   // precise mode: lo planes (0 = plain bf16)
+                   int q_lo_col, size_t kv_lo_off, int out_lo_col,     // precise mode: lo planes (0 = plain bf16)
+                   const KvPages pages) {
   constexpr int LPP = HD / 16;                   // lanes per kv position (4 / 8 / 16)
   constexpr int PPI = 32 / LPP;                  // positions per warp iteration
   pdl_trigger();
@@ -1070,8 +1074,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
       }
     }
   }
-  const __nv_bfloat16* kbase = kc + static_cast<size_t>(b * NKV + kvh) * Tmax * HD + slice * 16;
-  const __nv_bfloat16* vbase = vc + static_cast<size_t>(b * NKV + kvh) * Tmax * HD + slice * 16;
+  const __nv_bfloat16* kbase = kc + slice * 16;
+  const __nv_bfloat16* vbase = vc + slice * 16;
   const float LOG2E = 1.4426950408889634f;
   float m = -INFINITY, l = 0.f;
   float o[16];
@@ -1083,8 +1087,9 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
     float s = 0.f;
     uint4 kv[2], vv[2], vlo[2] = {};
     if (ok) {
-      const uint4* k4 = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(t) * HD);
-      const uint4* v4 = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(t) * HD);
+      const size_t trow = kv_row(pages, b, kvh, NKV, Tmax, t);
+      const uint4* k4 = reinterpret_cast<const uint4*>(kbase + trow * HD);
+      const uint4* v4 = reinterpret_cast<const uint4*>(vbase + trow * HD);
       kv[0] = __ldg(k4);
       kv[1] = __ldg(k4 + 1);
       vv[0] = __ldg(v4);          // V issued together with K: one memory round trip per iteration
@@ -1218,7 +1223,7 @@ __global__ void __launch_bounds__(DEC_SPLIT_THREADS)
 attn_decode_split_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                          const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* __restrict__ out, int ldo, int NKV,
                          int nrep, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap, int window,
-                         float* __restrict__ part, int* __restrict__ counters) {
+                         float* __restrict__ part, int* __restrict__ counters, const KvPages pages) {
   using Cfg = DecSplitCfg<HD>;
   constexpr int TP = Cfg::TP, STAGES = Cfg::STAGES, HB = Cfg::HB, TILE_BYTES = Cfg::TILE_BYTES;
   constexpr int KS = HD / 16;                    // k-steps of S = Q.K^T
@@ -1251,12 +1256,12 @@ attn_decode_split_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
   const int T = *t0_ptr + 1;                     // this step's token is already appended
   const int qpos = T - 1;
   const int kv_begin = (window > 0) ? max(0, qpos - window + 1) : 0;
-  const int len = T - kv_begin;
+  const int t_base = kv_begin & ~(TP - 1);       // tiles start on multiples of TP: they never straddle a cache page
+  const int len = T - t_base;
   const int per = (((len + nsplit - 1) / nsplit) + TP - 1) / TP * TP;     // positions per slice, whole tiles
-  const int t_lo = kv_begin + sp * per;
+  const int t_lo = t_base + sp * per;
   const int t_hi = min(T, t_lo + per);
   const int n_tiles = t_hi > t_lo ? (t_hi - t_lo + TP - 1) / TP : 0;
-  const int row0 = (b * NKV + kvh) * Tmax;
 
   const int g = lane >> 2, tq = lane & 3;        // MMA fragment coordinates: row g (= query head), column pair tq
   float m_row = -INFINITY, l_row = 0.f;          // row g's running max (log2 units) / this thread's share of the row sum
@@ -1267,11 +1272,11 @@ attn_decode_split_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
         const int st = i % STAGES;
         mbar_wait(&empty[st], ((i / STAGES) & 1) ^ 1);
         mbar_expect_tx(&full[st], 2 * TILE_BYTES);
-        const int t = t_lo + i * TP;
+        const int trow = static_cast<int>(kv_row(pages, b, kvh, NKV, Tmax, t_lo + i * TP));
 #pragma unroll
         for (int hb = 0; hb < HB; ++hb) {
-          tma_load_2d(sK + st * TILE_BYTES + hb * (TP * 128), &tmap_k, &full[st], hb * 64, row0 + t, kEvictFirst);
-          tma_load_2d(sV + st * TILE_BYTES + hb * (TP * 128), &tmap_v, &full[st], hb * 64, row0 + t, kEvictFirst);
+          tma_load_2d(sK + st * TILE_BYTES + hb * (TP * 128), &tmap_k, &full[st], hb * 64, trow, kEvictFirst);
+          tma_load_2d(sV + st * TILE_BYTES + hb * (TP * 128), &tmap_v, &full[st], hb * 64, trow, kEvictFirst);
         }
       }
     }
@@ -1297,7 +1302,7 @@ attn_decode_split_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
       const int st = i % STAGES;
       mbar_wait(&full[st], (i / STAGES) & 1);
       const int tpos = t_lo + i * TP + p0;       // absolute position of this warp's first row
-      if (tpos < t_hi) {
+      if (tpos < t_hi && tpos + 16 > kv_begin) {   // this warp's 16 positions intersect [kv_begin, t_hi)
         const uint32_t kb = smem_u32(sK + st * TILE_BYTES), vb = smem_u32(sV + st * TILE_BYTES);
         float sc[2][4];
 #pragma unroll
@@ -1324,12 +1329,13 @@ attn_decode_split_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
             float v = sc[nt][e];
             if (softcap > 0.f) v = softcap * LOG2E * tanhf(v * scale / softcap);
             else v *= sl2;
-            x[nt * 2 + e] = (tpos + nt * 8 + 2 * tq + e < t_hi) ? v : -INFINITY;
+            const int pos = tpos + nt * 8 + 2 * tq + e;
+            x[nt * 2 + e] = (pos < t_hi && pos >= kv_begin) ? v : -INFINITY;
           }
         float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float m_new = fmaxf(m_row, mx);    // finite: position tpos is valid for every row
+        const float m_new = fmaxf(m_row, mx);    // finite: at least one of the 16 positions is valid, for every row alike
         const float alpha = fast_exp2(m_row - m_new);
         float pe[4];
 #pragma unroll

@@ -276,6 +276,24 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // ---------------------------------------------------------------------------------------
+// KV-cache addressing: dense [B][NKV][Tmax][HD] planes, or pages of `page` positions picked through a block table
+// ---------------------------------------------------------------------------------------
+// Paged layout of one (layer, K|V) plane: [n_pages][NKV][page][HD]; table[b * max_lp + lp] = physical page of logical
+// page lp of batch row b.  `page` is a multiple of every kv tile width (32 / 64 / 128), so a tile never straddles pages
+// and a tile's rows are contiguous in the plane: one TMA box per tile either way.
+struct KvPages {
+  const int* table;   // nullptr = dense
+  int page, max_lp;
+};
+// row of position `pos` of (batch b, kv head kvh) inside the plane's [rows, HD] view
+__device__ __forceinline__ size_t kv_row(const KvPages& pg, int b, int kvh, int nkv, int Tmax, int pos) {
+  if (!pg.table) return static_cast<size_t>(b * nkv + kvh) * Tmax + pos;
+  const int lp = pos / pg.page;
+  const int phys = __ldg(pg.table + b * pg.max_lp + lp);
+  return (static_cast<size_t>(phys) * nkv + kvh) * pg.page + (pos - lp * pg.page);
+}
+
+// ---------------------------------------------------------------------------------------
 // small numeric helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -51,7 +51,7 @@ scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t
 __global__ void __launch_bounds__(256)
 attn_probs_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kc, float* __restrict__ out,
                   int B, int S, int NH, int NKV, int HD, int Tmax, const int* __restrict__ t0_ptr, float scale, float softcap,
-                  int causal, int window) {
+                  int causal, int window, const KvPages pages) {
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -62,13 +62,13 @@ attn_probs_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
   const int lo = window > 0 ? max(0, qpos - window + 1) : 0;
   const int hi = causal ? qpos : T - 1;
   const uint4* q4 = reinterpret_cast<const uint4*>(q + (static_cast<size_t>(b) * S + s) * ldq + h * HD);
-  const __nv_bfloat16* kb = kc + static_cast<size_t>(b * NKV + h / (NH / NKV)) * Tmax * HD;
+  const int kvh = h / (NH / NKV);
   float* o = out + row * T;
   float m = -INFINITY;
   for (int t = lane; t < T; t += 32) {
     float v = -INFINITY;
     if (t >= lo && t <= hi) {
-      const uint4* k4 = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(t) * HD);
+      const uint4* k4 = reinterpret_cast<const uint4*>(kc + kv_row(pages, b, kvh, NKV, Tmax, t) * HD);
       float acc = 0.f;
       for (int i = 0; i < HD / 8; ++i) {
         const uint4 a = __ldg(q4 + i), c = __ldg(k4 + i);

@@ -571,6 +571,16 @@ struct b2_cache {
   float* dec_part = nullptr;   // split-KV decode partials [max_batch][NH][DEC_MAX_SPLITS][HD+2]
   int* dec_cnt = nullptr;      // per (batch, kv head) arrival counters (self-resetting)
   int dec_splits = 0;
+  // paged cache: each (layer, K|V) plane is [n_pages][NKV][page][HD]; table[b][lp] = physical page of logical page lp
+  bool paged = false;
+  int page = 0, max_lp = 0, n_pages = 0;
+  int assigned_lp = 0, next_free = 0;      // logical pages handed out so far (every row alike), next unused physical page
+  bool user_table = false;                 // the caller supplied the block table (b2_cache_set_block_table)
+  int* table_dev = nullptr;
+  std::vector<int> table_host;
+  KvPages pages() const { return KvPages{paged ? table_dev : nullptr, page, max_lp}; }
+  int plane_rows() const { return static_cast<int>(plane / static_cast<size_t>(e_head_dim)); }
+  int e_head_dim = 1;
 };
 
 struct GraphKey {
@@ -847,6 +857,7 @@ extern "C" void b2_cache_destroy(b2_cache* c) {
   cudaFree(c->t0_dev);
   cudaFree(c->dec_part);
   cudaFree(c->dec_cnt);
+  cudaFree(c->table_dev);
   delete c;
 }
 
@@ -1008,10 +1019,12 @@ extern "C" int b2_finalize(b2_engine* e) {
 // ------------------------------------------------------------------------------------------
 // cache
 // ------------------------------------------------------------------------------------------
-extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_cache** out) {
+static int cache_create_impl(b2_engine* e, int max_batch, int max_tokens, int page_size, int n_pages, b2_cache** out) {
   if (!e || !out || max_batch <= 0 || max_tokens <= 0) return fail(B2_ERR_ARG, "bad cache arguments");
   if (max_tokens > e->cfg.max_positions)
     return fail(B2_ERR_ARG, "cache max_tokens %d exceeds the engine's RoPE table (%d positions)", max_tokens, e->cfg.max_positions);
+  const bool paged = page_size > 0;
+  if (paged && (page_size % 128 || page_size > 4096)) return fail(B2_ERR_ARG, "page_size %d must be a multiple of 128 (<= 4096)", page_size);
   CK(cudaSetDevice(e->device));
   static std::atomic<uint64_t> next_uid{1};
   b2_cache* c = new b2_cache();
@@ -1020,15 +1033,32 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   c->max_batch = max_batch;
   c->max_tokens = max_tokens;
   c->len = 0;
-  c->plane = static_cast<size_t>(max_batch) * e->nkv * max_tokens * e->cfg.head_dim;
+  c->e_head_dim = e->cfg.head_dim;
+  c->paged = paged;
+  if (paged) {
+    c->page = page_size;
+    c->max_lp = (max_tokens + page_size - 1) / page_size;
+    const long long full = static_cast<long long>(max_batch) * c->max_lp;
+    c->n_pages = n_pages > 0 ? n_pages : static_cast<int>(full);
+    if (c->n_pages < max_batch) c->n_pages = max_batch;               // at least one page per row
+    if (c->n_pages > full) c->n_pages = static_cast<int>(full);
+    c->plane = static_cast<size_t>(c->n_pages) * e->nkv * page_size * e->cfg.head_dim;
+    c->table_host.assign(static_cast<size_t>(max_batch) * c->max_lp, 0);
+  } else {
+    c->plane = static_cast<size_t>(max_batch) * e->nkv * max_tokens * e->cfg.head_dim;
+  }
   c->pf = e->cfg.precise ? 2 : 1;
   const size_t bytes = c->plane * c->pf * 2 * e->cfg.num_hidden_layers * 2;
-  if (c->pf == 2 && c->plane > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "precise-mode cache plane too large"); }
+  if (c->plane > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "cache plane of %zu elements exceeds the 2^31 rows*HD a tensor map row index covers", c->plane); }
   auto alloc = [&]() -> int {
     CK(cudaMalloc(&c->kv, bytes));
     CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
     CK(cudaMalloc(&c->t0_dev, 4));
     CK(cudaMemset(c->t0_dev, 0, 4));
+    if (paged) {
+      CK(cudaMalloc(&c->table_dev, c->table_host.size() * 4));
+      CK(cudaMemset(c->table_dev, 0, c->table_host.size() * 4));
+    }
     if (!e->cfg.precise) {
       c->dec_splits = decode_splits(max_batch, e->nkv, max_tokens);
       CK(cudaMalloc(&c->dec_part, decode_part_floats(max_batch, e->nh, e->cfg.head_dim) * 4));
@@ -1047,6 +1077,80 @@ extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_c
   *out = c;
   return B2_OK;
 }
+extern "C" int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_cache** out) {
+  return cache_create_impl(e, max_batch, max_tokens, 0, 0, out);
+}
+extern "C" int b2_cache_create_paged(b2_engine* e, int max_batch, int max_tokens, int page_size, int n_pages, b2_cache** out) {
+  if (page_size <= 0) return fail(B2_ERR_ARG, "page_size must be positive");
+  return cache_create_impl(e, max_batch, max_tokens, page_size, n_pages, out);
+}
+extern "C" int b2_cache_set_block_table(b2_cache* c, const int32_t* table_host, int n_entries) {
+  if (!c || !table_host) return fail(B2_ERR_ARG, "null argument");
+  if (!c->paged) return fail(B2_ERR_ARG, "not a paged cache");
+  if (!c->e) return fail(B2_ERR_STATE, "the cache's engine has been destroyed");
+  if (c->len != 0) return fail(B2_ERR_STATE, "the block table can only be replaced while the cache is empty");
+  if (n_entries != static_cast<int>(c->table_host.size()))
+    return fail(B2_ERR_ARG, "block table has %d entries, expected max_batch * max_logical_pages = %zu", n_entries, c->table_host.size());
+  std::vector<uint8_t> seen(c->n_pages, 0);
+  for (int i = 0; i < n_entries; ++i) {
+    const int pg = table_host[i];
+    if (pg < 0 || pg >= c->n_pages || seen[pg]) return fail(B2_ERR_ARG, "block table entry %d = %d is out of range or used twice (pool of %d pages)", i, pg, c->n_pages);
+    seen[pg] = 1;
+  }
+  CK(cudaSetDevice(c->e->device));
+  c->table_host.assign(table_host, table_host + n_entries);
+  CK(cudaMemcpy(c->table_dev, c->table_host.data(), c->table_host.size() * 4, cudaMemcpyHostToDevice));
+  c->user_table = true;
+  c->assigned_lp = c->max_lp;
+  return B2_OK;
+}
+extern "C" int b2_cache_info(const b2_cache* c, int32_t* page_size, int32_t* n_pages, int32_t* pages_in_use) {
+  if (!c) return fail(B2_ERR_ARG, "null cache");
+  if (page_size) *page_size = c->paged ? c->page : 0;
+  if (n_pages) *n_pages = c->paged ? c->n_pages : 0;
+  if (pages_in_use) *pages_in_use = c->paged ? (c->user_table ? ((c->len + c->page - 1) / c->page) * c->max_batch : c->next_free) : 0;
+  return B2_OK;
+}
+
+// Paged cache: make sure logical pages [0, ceil(tokens / page)) of every row have a physical page.  Pages are handed out
+// row-interleaved (logical page lp of row b -> physical page lp * max_batch + b), so consecutive logical pages of a
+// sequence are max_batch pages apart in the pool -- the block-table indirection is always exercised.  A pool that runs
+// out grows by doubling (new allocation + plane-wise copy; the captured decode graphs of this cache are dropped).
+static int cache_ensure_pages(b2_cache* c, int tokens, cudaStream_t st) {
+  if (!c->paged) return B2_OK;
+  const int need_lp = (tokens + c->page - 1) / c->page;
+  if (need_lp <= c->assigned_lp) return B2_OK;
+  if (c->user_table) return fail(B2_ERR_STATE, "internal: user block table covers every logical page");
+  b2_engine* e = c->e;
+  const long long need_pages = static_cast<long long>(need_lp) * c->max_batch;
+  if (need_pages > c->n_pages) {
+    long long nn = c->n_pages;
+    while (nn < need_pages) nn *= 2;
+    const long long full = static_cast<long long>(c->max_batch) * c->max_lp;
+    if (nn > full) nn = full;
+    const size_t new_plane = static_cast<size_t>(nn) * e->nkv * c->page * e->cfg.head_dim;
+    if (new_plane > 0x7fffffffull) return fail(B2_ERR_ARG, "paged cache cannot grow to %lld pages (plane index range)", nn);
+    const int nplanes = e->cfg.num_hidden_layers * 2 * c->pf;
+    bf16* nkv = nullptr;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMalloc(&nkv, new_plane * nplanes * 2));
+    CK(cudaMemset(nkv, 0, new_plane * nplanes * 2));
+    for (int i = 0; i < nplanes; ++i)
+      CK(cudaMemcpy(nkv + static_cast<size_t>(i) * new_plane, c->kv + static_cast<size_t>(i) * c->plane, c->plane * 2, cudaMemcpyDeviceToDevice));
+    CK(cudaDeviceSynchronize());
+    cudaFree(c->kv);
+    c->kv = nkv;
+    c->plane = new_plane;
+    c->n_pages = static_cast<int>(nn);
+    for (auto it = e->graphs.begin(); it != e->graphs.end();) { auto cur = it++; if (cur->first.cache_uid == c->uid) drop_graph(e, cur); }
+  }
+  for (int lp = c->assigned_lp; lp < need_lp; ++lp)
+    for (int b = 0; b < c->max_batch; ++b) c->table_host[static_cast<size_t>(b) * c->max_lp + lp] = c->next_free++;
+  c->assigned_lp = need_lp;
+  CK(cudaMemcpyAsync(c->table_dev, c->table_host.data(), c->table_host.size() * 4, cudaMemcpyHostToDevice, st));
+  return B2_OK;
+}
 extern "C" int b2_cache_len(const b2_cache* c) { return c ? c->len : fail(B2_ERR_ARG, "null cache"); }
 extern "C" int b2_cache_reset(b2_cache* c) {
   if (!c) return fail(B2_ERR_ARG, "null cache");
@@ -1055,6 +1159,7 @@ extern "C" int b2_cache_reset(b2_cache* c) {
   CK(cudaStreamSynchronize(c->e->stream));
   CK(cudaDeviceSynchronize());
   c->len = 0;
+  if (c->paged && !c->user_table) c->assigned_lp = c->next_free = 0;   // every page goes back to the pool
   CK(cudaMemset(c->t0_dev, 0, 4));
   CK(cudaDeviceSynchronize());
   return B2_OK;

@@ -43,7 +43,8 @@ struct GemmParams {
   int q_cols, kv_cols, head_dim, S, Tmax, nkv;
   __nv_bfloat16* q_out;
   int ldq;
-  __nv_bfloat16* k_cache;  // [B][NKV][Tmax][HD] (this layer)
+  KvPages pages;           // block table of a paged cache (table == nullptr: dense)
+  __nv_bfloat16* k_cache;  // [B][NKV][Tmax][HD] (this layer), or the layer's paged plane [n_pages][NKV][page][HD]
   __nv_bfloat16* v_cache;
   const int* t0_ptr;       // device scalar: tokens already in the cache
   const int* pos_ids;      // optional [S] caller position_ids for RoPE (llama3.2_model_numpy.py:657); nullptr = t0 + s.
@@ -296,7 +297,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
           rope = false;
         }
         const int kvh = n1 / HD;
-        dst = base + (static_cast<size_t>(b * p.nkv + kvh) * p.Tmax + pos) * HD;
+        dst = base + kv_row(p.pages, b, kvh, p.nkv, p.Tmax, pos) * HD;
         lo_off = p.kv_lo_off;
       }
       __syncwarp();

@@ -19,4 +19,4 @@ for f in gpurun_out/r02_bench_*.json; do python -c "
 import json,sys
 d=json.loads(open('$f').read().strip().splitlines()[-1]); print('$f', d.get('metric'), round(d['value'],1), round(d['ms_per_step'],3), (d.get('precise') or {}).get('value'), (d.get('cpu_baseline_long') or {}))"; done
 timeout 120 tools/mb/pipes 2>&1 | tail -30 > gpurun_out/r02_pipe_microbench.txt; tail -12 gpurun_out/r02_pipe_microbench.txt
-tools/r2_ncu.sh
+tools/r2_ncu.sh prefill
