@@ -91,6 +91,18 @@ int b2_cache_create(b2_engine* e, int max_batch, int max_tokens, b2_cache** out)
 void b2_cache_destroy(b2_cache* c);
 int b2_cache_len(const b2_cache* c);   /* KVCache.num_items() */
 int b2_cache_reset(b2_cache* c);
+/* Paged variant: every (layer, K|V) plane is a pool of n_pages pages of page_size positions ([n_pages][NKV][page][HD]) and a
+ * block table [max_batch][ceil(max_tokens / page_size)] maps a sequence's logical pages to physical ones (the layout of
+ * vLLM-style paged attention).  page_size: a multiple of 128.  n_pages: 0 = enough for max_tokens
+ * of every row; smaller = the pool starts there and doubles on demand (allocation + plane-wise copy), i.e. memory follows
+ * the tokens actually cached instead of max_tokens.  Pages are handed out row-interleaved as the sequences grow.
+ * b2_cache_len / reset / read / destroy and b2_forward work on both kinds. */
+int b2_cache_create_paged(b2_engine* e, int max_batch, int max_tokens, int page_size, int n_pages, b2_cache** out);
+/* Replace the block table of an EMPTY paged cache (host int32 [max_batch * max_logical_pages], every entry a distinct page
+ * in [0, n_pages)): lets a caller place pages itself (tests use a shuffled permutation). */
+int b2_cache_set_block_table(b2_cache* c, const int32_t* table_host, int n_entries);
+/* page_size (0 = dense cache), pool size in pages, pages currently handed out */
+int b2_cache_info(const b2_cache* c, int32_t* page_size, int32_t* n_pages, int32_t* pages_in_use);
 /* copy layer `layer`'s K or V ([batch][NKV][len][HD], bf16) to a device buffer -- KVCache.key_cache[i] */
 int b2_cache_read(const b2_cache* c, int layer, int which /*0=K,1=V*/, int batch, void* dev_out);
 

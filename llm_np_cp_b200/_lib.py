@@ -46,6 +46,9 @@ SYMBOLS = [
     ("b2_load_weight", _I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I, _I]),
     ("b2_finalize", _I, [_P]),
     ("b2_cache_create", _I, [_P, _I, _I, C.POINTER(_P)]),
+    ("b2_cache_create_paged", _I, [_P, _I, _I, _I, _I, C.POINTER(_P)]),
+    ("b2_cache_set_block_table", _I, [_P, C.POINTER(C.c_int32), _I]),
+    ("b2_cache_info", _I, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("b2_cache_destroy", None, [_P]),
     ("b2_cache_len", _I, [_P]),
     ("b2_cache_reset", _I, [_P]),

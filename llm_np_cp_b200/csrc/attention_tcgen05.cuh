@@ -36,7 +36,8 @@ struct AttnParams {
   int v_lbo, v_sbo;      // V (MN-major) descriptor byte offsets; 0 = defaults (BNKV*128, 1024)
   // precise (hi/lo split-bf16) mode: every bf16 operand x is carried as x_hi + x_lo
   int q_lo_col;          // column offset of the lo plane inside a q row (= NH*HD), 0 = not precise
-  int kv_lo_row;         // row offset of the lo plane inside the K/V tensor maps (= B_max*NKV*Tmax)
+  int kv_lo_row;         // row offset of the lo plane inside the K/V tensor maps (= rows of one plane)
+  int kv_plane_rows;     // rows of one K/V plane (0 = B*NKV*Tmax, the dense layout of the single-kernel test entry points)
   int out_lo_col;        // column offset of the lo plane inside an output row
   unsigned long long* trace;   // bring-up: clock64() timeline of CTA (0,0,0); nullptr = off
   unsigned long long* cta_trace;   // diagnostics: per CTA {globaltimer at start, at end, smid}; nullptr = off

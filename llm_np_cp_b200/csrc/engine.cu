@@ -414,7 +414,8 @@ static int attn_prefill(const bf16* q, int ldq, const bf16* kc, const bf16* vc, 
   const bool precise = p.q_lo_col != 0;
   const bool co = !precise && !force_single && (HD == 64 || HD == 128) && p.S > ATT_BM && !p.v_lbo && !p.v_sbo;
   const int planes = precise ? 2 : 1;
-  const uint64_t kv_rows = static_cast<uint64_t>(planes) * (precise ? p.kv_lo_row : static_cast<uint64_t>(p.B) * p.NKV * p.Tmax);
+  const uint64_t plane_rows = p.kv_plane_rows ? static_cast<uint64_t>(p.kv_plane_rows) : static_cast<uint64_t>(p.B) * p.NKV * p.Tmax;
+  const uint64_t kv_rows = static_cast<uint64_t>(planes) * (precise ? p.kv_lo_row : plane_rows);
   const int bnkv = precise ? (HD <= 128 ? 64 : 32) : (co ? (HD == 64 ? 128 : 64) : (HD <= 128 ? 128 : 64));
   CKR(make_tmap(&tq, q, static_cast<uint64_t>(p.B) * p.S, static_cast<uint64_t>(planes) * p.NH * HD, ldq, ATT_BM));
   CKR(make_tmap(&tk, kc, kv_rows, HD, HD, bnkv));
@@ -453,16 +454,16 @@ static size_t decode_part_floats(int B, int NH, int HD) { return static_cast<siz
 template <int HD>
 static int launch_decode_split(const bf16* q, int ldq, const bf16* kc, const bf16* vc, bf16* out, int ldo, int B, int NKV,
                                int nrep, int Tmax, const int* t0_ptr, float scale, float softcap, int window, float* part,
-                               int* cnt, int nsplit, cudaStream_t st) {
+                               int* cnt, int nsplit, cudaStream_t st, const KvPages& pages, int plane_rows) {
   auto kern = attn_decode_split_kernel<HD>;
   static std::atomic<uint64_t> attr{0};
   CKR(smem_attr_once(kern, DecSplitCfg<HD>::SMEM_BYTES, attr));
   CUtensorMap tk, tv;
-  const uint64_t kv_rows = static_cast<uint64_t>(B) * NKV * Tmax;
+  const uint64_t kv_rows = plane_rows ? static_cast<uint64_t>(plane_rows) : static_cast<uint64_t>(B) * NKV * Tmax;
   CKR(make_tmap(&tk, kc, kv_rows, HD, HD, 64));
   CKR(make_tmap(&tv, vc, kv_rows, HD, HD, 64));
   CK(launch_k(kern, dim3(nsplit, NKV, B), dim3(DEC_SPLIT_THREADS), DecSplitCfg<HD>::SMEM_BYTES, st, tk, tv, q, ldq, out, ldo,
-              NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt));
+              NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, pages));
   return B2_OK;
 }
 
@@ -471,18 +472,18 @@ static int launch_decode_split(const bf16* q, int ldq, const bf16* kc, const bf1
 static int attn_decode(const bf16* q, int ldq, const bf16* kc, const bf16* vc, bf16* out, int ldo, int B, int NH,
                        int NKV, int HD, int Tmax, const int* t0_ptr, float scale, float softcap, int window,
                        cudaStream_t st, int q_lo_col = 0, size_t kv_lo_off = 0, int out_lo_col = 0, float* part = nullptr,
-                       int* cnt = nullptr, int nsplit = 0) {
+                       int* cnt = nullptr, int nsplit = 0, KvPages pages = KvPages{nullptr, 0, 0}, int plane_rows = 0) {
   const int nrep = NH / NKV;
   if (part && cnt && nsplit > 0 && !q_lo_col && nrep >= 1 && nrep <= DEC_MAX_NREP) {
-    if (HD == 64) return launch_decode_split<64>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st);
-    if (HD == 128) return launch_decode_split<128>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st);
-    if (HD == 256) return launch_decode_split<256>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st);
+    if (HD == 64) return launch_decode_split<64>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st, pages, plane_rows);
+    if (HD == 128) return launch_decode_split<128>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st, pages, plane_rows);
+    if (HD == 256) return launch_decode_split<256>(q, ldq, kc, vc, out, ldo, B, NKV, nrep, Tmax, t0_ptr, scale, softcap, window, part, cnt, nsplit, st, pages, plane_rows);
   }
   const int grid = (B * NH + 3) / 4;
 #define DEC(HD_)                                                                                              \
   if (HD == HD_) {                                                                                            \
     CK(launch_k(attn_decode_kernel<HD_>, dim3(grid), dim3(128), 0, st, q, ldq, kc, vc, out, ldo, B, NH, NKV, Tmax, t0_ptr, \
-                scale, softcap, window, q_lo_col, kv_lo_off, out_lo_col));                                    \
+                scale, softcap, window, q_lo_col, kv_lo_off, out_lo_col, pages));                             \
     return B2_OK;                                                                                             \
   }
   DEC(64) DEC(128) DEC(256)
@@ -1049,7 +1050,8 @@ static int cache_create_impl(b2_engine* e, int max_batch, int max_tokens, int pa
   }
   c->pf = e->cfg.precise ? 2 : 1;
   const size_t bytes = c->plane * c->pf * 2 * e->cfg.num_hidden_layers * 2;
-  if (c->plane > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "cache plane of %zu elements exceeds the 2^31 rows*HD a tensor map row index covers", c->plane); }
+  if (c->pf == 2 && c->plane > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "precise-mode cache plane too large"); }
+  if (c->plane / e->cfg.head_dim > 0x7fffffffull) { delete c; return fail(B2_ERR_ARG, "cache plane has more rows than a tensor-map coordinate covers"); }
   auto alloc = [&]() -> int {
     CK(cudaMalloc(&c->kv, bytes));
     CK(cudaMemset(c->kv, 0, bytes));   // rows past the valid length feed P.V with weight 0: must stay finite
@@ -1129,7 +1131,7 @@ static int cache_ensure_pages(b2_cache* c, int tokens, cudaStream_t st) {
     const long long full = static_cast<long long>(c->max_batch) * c->max_lp;
     if (nn > full) nn = full;
     const size_t new_plane = static_cast<size_t>(nn) * e->nkv * c->page * e->cfg.head_dim;
-    if (new_plane > 0x7fffffffull) return fail(B2_ERR_ARG, "paged cache cannot grow to %lld pages (plane index range)", nn);
+    if (c->pf == 2 && new_plane > 0x7fffffffull) return fail(B2_ERR_ARG, "precise-mode paged cache cannot grow to %lld pages", nn);
     const int nplanes = e->cfg.num_hidden_layers * 2 * c->pf;
     bf16* nkv = nullptr;
     CK(cudaStreamSynchronize(st));
@@ -1176,6 +1178,19 @@ extern "C" int b2_cache_read(const b2_cache* c, int layer, int which, int batch,
   if (c->len == 0) return B2_OK;                 // nothing cached: a zero-width copy is an error in CUDA
   CK(cudaDeviceSynchronize());                   // forwards may still be running on non-blocking streams
   const bf16* src = which ? cache_v(c, layer) : cache_k(c, layer);
+  if (c->paged) {   // gather the pages of every row: one 2-D copy (NKV slabs) per (row, logical page)
+    const size_t hd = g.head_dim;
+    for (int b = 0; b < batch; ++b)
+      for (int lp = 0; lp * c->page < c->len; ++lp) {
+        const int rows = (c->len - lp * c->page) < c->page ? (c->len - lp * c->page) : c->page;
+        const int phys = c->table_host[static_cast<size_t>(b) * c->max_lp + lp];
+        CK(cudaMemcpy2DAsync(static_cast<bf16*>(dev_out) + (static_cast<size_t>(b) * c->e->nkv * c->len + static_cast<size_t>(lp) * c->page) * hd,
+                             static_cast<size_t>(c->len) * hd * 2, src + static_cast<size_t>(phys) * c->e->nkv * c->page * hd,
+                             static_cast<size_t>(c->page) * hd * 2, static_cast<size_t>(rows) * hd * 2, c->e->nkv, cudaMemcpyDeviceToDevice, 0));
+      }
+    CK(cudaDeviceSynchronize());
+    return B2_OK;
+  }
   // [batch*NKV] slabs of [len, HD] out of [max_tokens, HD]
   CK(cudaMemcpy2DAsync(dev_out, static_cast<size_t>(c->len) * g.head_dim * 2, src,
                        static_cast<size_t>(c->max_tokens) * g.head_dim * 2, static_cast<size_t>(c->len) * g.head_dim * 2,
@@ -1358,7 +1373,7 @@ static int run_decode_fused(b2_engine* e, b2_cache* cache, cudaStream_t st, cons
       p.q_cols = e->q_cols; p.kv_cols = e->kv_cols; p.head_dim = HD; p.S = 1; p.Tmax = cache->max_tokens; p.nkv = e->nkv;
       p.q_out = e->q; p.ldq = e->q_cols;
       p.k_cache = cache_k(cache, li); p.v_cache = cache_v(cache, li);
-      p.t0_ptr = cache->t0_dev; p.pos_ids = fa.pos_ids; p.rope_cos = e->rope_cos; p.rope_sin = e->rope_sin;
+      p.t0_ptr = cache->t0_dev; p.pages = cache->pages(); p.pos_ids = fa.pos_ids; p.rope_cos = e->rope_cos; p.rope_sin = e->rope_sin;
       consumer(p);
       if (HD == SK_BN) CKR(eng_gemm_sk(e, st, EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
       else CKR(eng_gemm(e, st, HD, EPI_QKV_ROPE, e->xn, H, Ly.wqkv, p));
@@ -1366,7 +1381,7 @@ static int run_decode_fused(b2_engine* e, b2_cache* cache, cudaStream_t st, cons
     const int window = (c.sliding_window > 0 && e->sliding[li]) ? c.sliding_window : 0;
     CKR(attn_decode(e->q, e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, e->q_cols, M, e->nh, e->nkv, HD,
                     cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st, 0, 0, 0, cache->dec_part,
-                    cache->dec_cnt, cache->dec_splits));
+                    cache->dec_cnt, cache->dec_splits, cache->pages(), cache->plane_rows()));
     e->st.launches++;
     {
       GemmParams p = base_params(M, H, e->q_cols);          // x += attn . Wo^T; xn = bf16(x * g_post); ss
@@ -1444,6 +1459,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
       p.k_cache = cache_k(cache, li);
       p.v_cache = cache_v(cache, li);
       p.t0_ptr = cache->t0_dev;
+      p.pages = cache->pages();
       p.pos_ids = fa.pos_ids;
       p.rope_cos = e->rope_cos;
       p.rope_sin = e->rope_sin;
@@ -1458,14 +1474,14 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
       CK(launch_k(attn_probs_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, st, static_cast<const bf16*>(e->q),
                   pf * e->q_cols, static_cast<const bf16*>(cache_k(cache, li)), fa.attn_probs + static_cast<size_t>(li) * rows * T_total,
                   B, S, e->nh, e->nkv, HD, cache->max_tokens, static_cast<const int*>(cache->t0_dev),
-                  scale, c.attn_logit_softcap, causal, window));
+                  scale, c.attn_logit_softcap, causal, window, cache->pages()));
       e->st.launches++;
     }
     if (decode) {
       CKR(attn_decode(e->q, pf * e->q_cols, cache_k(cache, li), cache_v(cache, li), e->att, pf * e->q_cols, B, e->nh,
                       e->nkv, HD, cache->max_tokens, cache->t0_dev, scale, c.attn_logit_softcap, window, st,
                       c.precise ? e->q_cols : 0, c.precise ? cache->plane : 0, c.precise ? e->q_cols : 0, cache->dec_part,
-                      cache->dec_cnt, cache->dec_splits));
+                      cache->dec_cnt, cache->dec_splits, cache->pages(), cache->plane_rows()));
       e->st.launches++;
     } else {
       AttnParams a;
@@ -1473,10 +1489,12 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
       a.B = B; a.S = S; a.NH = e->nh; a.NKV = e->nkv; a.Tmax = cache->max_tokens;
       a.t0_ptr = cache->t0_dev; a.scale = scale; a.softcap = c.attn_logit_softcap; a.causal = causal; a.window = window;
       a.out = e->att; a.ldo = pf * e->q_cols;
+      a.pages = cache->pages();
+      a.kv_plane_rows = cache->plane_rows();
       if (c.precise) {
         a.q_lo_col = e->q_cols;
         a.out_lo_col = e->q_cols;
-        a.kv_lo_row = cache->max_batch * e->nkv * cache->max_tokens;
+        a.kv_lo_row = cache->plane_rows();
       }
       const double T = cache->len + S;
       const double pairs = causal ? (static_cast<double>(S) * (S + 1) / 2 + static_cast<double>(S) * cache->len) : S * T;
@@ -1619,6 +1637,7 @@ extern "C" int b2_forward_ex(b2_engine* e, b2_cache* cache, const b2_forward_arg
                                 "is not supported by the reference path (set always_causal for chunked prefill)", S, kc->len);
   }
   CKR(ensure_ws(e, B * S, B));
+  CKR(cache_ensure_pages(kc, kc->len + S, st));        // paged cache: physical pages for the positions this call appends
   FwdArgs fa;
   fa.ids = ua.ids; fa.embeds = ua.inputs_embeds; fa.pos_ids = ua.position_ids;
   fa.B = B; fa.S = S; fa.logits_mode = logits_mode; fa.logits = ua.logits; fa.hidden = ua.hidden; fa.attn_probs = ua.attn_probs;

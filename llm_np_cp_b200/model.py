@@ -83,21 +83,49 @@ class _LayerViews:
 
 
 class KVCache:
-    """KVCache() of the reference (llama3.2_model_numpy.py:311-340) backed by a preallocated device
-    buffer.  ``KVCache()`` takes no arguments there; here capacity is fixed at first use
-    (``max_tokens`` defaults to the model's RoPE-table length capped at 8192)."""
+    """KVCache() of the reference (llama3.2_model_numpy.py:311-340) backed by device memory owned by the engine.
 
-    def __init__(self, max_batch: Optional[int] = None, max_tokens: Optional[int] = None):
+    ``KVCache()`` takes no arguments there.  Here, with no ``max_tokens`` the cache is PAGED (``page_size`` positions per
+    page, block table per sequence) and its pool grows on demand, so memory follows the tokens actually cached -- the
+    reference's lists grow the same way; with ``max_tokens`` it is one dense preallocated ``[L][2][B][NKV][max_tokens][HD]``
+    buffer (what bench.py uses), or a paged pool of ``n_pages`` pages when ``paged=True``."""
+
+    def __init__(self, max_batch: Optional[int] = None, max_tokens: Optional[int] = None, paged: Optional[bool] = None,
+                 page_size: int = 128, n_pages: Optional[int] = None):
         self.max_batch, self.max_tokens = max_batch, max_tokens
+        self.paged = (max_tokens is None) if paged is None else bool(paged)
+        self.page_size, self.n_pages = page_size, n_pages
+        self._table = None
         self._h = None
         self._model = None
+
+    def set_block_table(self, table):
+        """Place pages yourself: int32 [max_batch, ceil(max_tokens / page_size)] of distinct physical pages.  Applied when
+        the cache binds to a model (first use); only valid for ``paged=True`` caches with explicit sizes."""
+        self._table = np.ascontiguousarray(table, dtype=np.int32)
+
+    def pool_info(self):
+        """(page_size, pages in the pool, pages handed out); page_size 0 = dense cache."""
+        if self._h is None:
+            return (self.page_size if self.paged else 0, 0, 0)
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        check(_lib.lib().b2_cache_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def _bind(self, model, batch):
         if self._h is None:
             mb = self.max_batch or batch
             mt = self.max_tokens or min(model._cfg.max_positions, 8192)
             h = C.c_void_p()
-            check(_lib.lib().b2_cache_create(model._h, mb, mt, C.byref(h)))
+            if self.paged:
+                # no explicit pool size: start with one page per sequence and let the engine double the pool as needed
+                npg = self.n_pages if self.n_pages is not None else (mb if self.max_tokens is None else 0)
+                check(_lib.lib().b2_cache_create_paged(model._h, mb, mt, self.page_size, npg, C.byref(h)))
+                if self._table is not None:
+                    t = self._table.reshape(-1)
+                    check(_lib.lib().b2_cache_set_block_table(h, t.ctypes.data_as(C.POINTER(C.c_int32)), t.size))
+            else:
+                check(_lib.lib().b2_cache_create(model._h, mb, mt, C.byref(h)))
             self._h, self._model, self.max_batch, self.max_tokens = h, model, mb, mt
         elif self._model is not model:
             raise ValueError("KVCache is bound to a different model")

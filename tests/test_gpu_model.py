@@ -76,6 +76,67 @@ def test_decode_with_cache_vs_reference_golden(name):
     assert len(list(cache.key_cache)) == cfg.num_hidden_layers and len(M.KVCache().key_cache) == 0
 
 
+@pytest.mark.parametrize("name", ["llama_tiny_decode", "gemma2_tiny_decode"])
+@pytest.mark.parametrize("kind", ["default", "paged_full_pool", "paged_small_pool"])
+def test_paged_cache_vs_reference_golden(name, kind):
+    """Paged KV cache (block table + page pool) against the reference's outputs: KVCache() with no
+    arguments (paged, pool growing from one page per sequence), an explicit full pool, and a pool that must grow."""
+    meta, arr = load_golden(name)
+    cfg, w, model = build(meta)
+    S, dec = meta["S"], meta["decode_steps"]
+    cache = {"default": M.KVCache(), "paged_full_pool": M.KVCache(max_tokens=512, paged=True),
+             "paged_small_pool": M.KVCache(max_tokens=1024, paged=True, n_pages=1)}[kind]
+    assert cache.paged
+    _, logits, cache2, _, _ = model(arr["ids"][:, :S], use_cache=True, kv_cache=cache)
+    assert cache2 is cache and cache.num_items() == S
+    check_close(logits.cpu().numpy(), arr["logits"], f"{name} paged({kind}) prefill logits")
+    for i in range(dec):
+        _, lg, _, _, _ = model(arr["ids"][:, S + i:S + i + 1], use_cache=True, kv_cache=cache)
+        check_close(lg.cpu().numpy(), arr["decode_logits"][i], f"{name} paged({kind}) step {i}")
+    page, pool, used = cache.pool_info()
+    B = arr["ids"].shape[0]
+    assert page == 128 and used == B and pool >= B          # one logical page per sequence so far
+    assert tuple(cache.key_cache[0].shape) == (B, cfg.num_key_value_heads, S + dec, cfg.head_dim)
+
+
+@pytest.mark.parametrize("family", ["llama", "gemma2"])
+def test_paged_cache_is_bit_identical_to_dense(family):
+    """Same kernels, same data, different addresses: a paged cache -- with a SHUFFLED block table, and with a pool that grows
+    twice while the sequence crosses page boundaries -- gives bit-identical logits and cache contents to the dense cache,
+    through chunked prefill over several pages, graph-replayed decode steps across a page boundary, and cache.key_cache."""
+    cfg = (O.gemma2_config if family == "gemma2" else O.llama_config)("tiny")
+    w = O.synth_weights(cfg, 6, 0.08, 0.1)
+    cls = M.Gemma2ForCausalLM if family == "gemma2" else M.LlamaForCausalLM
+    model = cls(M.AttributeDict(cfg), w, always_causal=True)          # chunked prefill needs the HF mask semantics
+    B, T0, T1, dec = 2, 300, 507, 8                                    # 507 + 8 crosses the 512 = 4-page boundary
+    ids = np.random.default_rng(21).integers(0, cfg.vocab_size, (B, T1 + dec))
+    rng = np.random.default_rng(5)
+
+    def run(cache):
+        model.set_decode_graph(True)
+        outs = [model(ids[:, :T0], use_cache=True, kv_cache=cache, output_hidden_states=False)[1],
+                model(ids[:, T0:T1], use_cache=True, kv_cache=cache, output_hidden_states=False)[1]]
+        for t in range(T1, T1 + dec):
+            outs.append(model(ids[:, t:t + 1], use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=2)[1])
+        model.set_decode_graph(False)
+        return outs, cache.key_cache[1].clone(), cache.value_cache[0].clone()
+
+    dense = run(M.KVCache(max_batch=B, max_tokens=1024))
+    shuffled = M.KVCache(max_batch=B, max_tokens=1024, paged=True)
+    shuffled.set_block_table(rng.permutation(B * 8).reshape(B, 8))
+    growing = M.KVCache(max_batch=B, max_tokens=1024, paged=True, n_pages=2)
+    for name, cache in (("shuffled block table", shuffled), ("growing pool", growing)):
+        got = run(cache)
+        for a, b in zip(dense[0], got[0]):
+            assert torch.equal(a, b), name
+        assert torch.equal(dense[1], got[1]) and torch.equal(dense[2], got[2]), name
+    assert growing.pool_info()[1] >= 2 * 5 and growing.pool_info()[2] == 2 * 5      # 5 logical pages per row in use
+    with pytest.raises(ValueError):
+        bad = M.KVCache(max_batch=B, max_tokens=1024, paged=True)
+        bad.set_block_table(np.zeros((B, 8), dtype=np.int32))                       # a page used twice
+        model(ids[:, :4], use_cache=True, kv_cache=bad, output_hidden_states=False)
+
+
 def test_decode_graph_matches_plain():
     meta, arr = load_golden("llama_tiny_decode")
     cfg, w, model = build(meta)
