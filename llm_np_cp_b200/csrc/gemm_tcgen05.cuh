@@ -297,7 +297,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const CUtenso
           rope = false;
         }
         const int kvh = n1 / HD;
-        dst = base + kv_row(p.pages, b, kvh, p.nkv, p.Tmax, pos) * HD;
+        // rows past M (the tile's padding) have no batch row: no block-table lookup for them (they store nothing)
+        dst = base + (row_ok ? kv_row(p.pages, b, kvh, p.nkv, p.Tmax, pos) : 0) * HD;
         lo_off = p.kv_lo_off;
       }
       __syncwarp();
