@@ -1,5 +1,8 @@
 """Bring-up diagnostics (run on the GPU box): each stage in its own process so a trap cannot hide the rest.
-usage: python tools/gpu_diag.py <stage>     stages: info gemm attn attn_variants"""
+usage: python tools/gpu_diag.py <stage>     stages: info gemm attn attn_variants
+The timeline stages (attn_trace, attn_cta) read B2_ATT_TRACE / B2_ATT_CTATRACE, which only a diagnostics build honours:
+    B2_DEFINES=-DB2_DIAG python llm_np_cp_b200/build.py --force
+and they trace round 1's one-tile-per-CTA attention kernel (run them with B2_ATTN_CO_ONESHOT=1)."""
 import math
 import os
 import sys
