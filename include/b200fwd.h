@@ -142,6 +142,14 @@ int b2_forward_ex(b2_engine* e, b2_cache* cache, const b2_forward_args* args);
 #define B2_NCCL_ID_BYTES 128
 int b2_tp_unique_id(void* id_out);
 int b2_tp_init(b2_engine* e, const void* id);
+/* Peer-memory (NVLink P2P) path of the tensor-parallel decode step: each rank exports one buffer as a cudaIpc handle
+ * (B2_IPC_HANDLE_BYTES bytes), the caller all-gathers the handles in rank order, each rank maps its peers.  Afterwards the
+ * few-row Llama path replaces ncclAllReduce + RMSNorm by ONE kernel that barriers through flags in peer memory, sums the
+ * ranks' partial planes straight over NVLink in rank order, adds the residual and normalises.  Optional: without these two
+ * calls everything goes through NCCL. */
+#define B2_IPC_HANDLE_BYTES 64
+int b2_tp_ipc_handle(b2_engine* e, void* handle_out);
+int b2_tp_set_peers(b2_engine* e, const void* handles_in_rank_order, int n_handles);
 /* HF layer_types: is_sliding[i] != 0 => layer i applies cfg.sliding_window (default without this call: even layers,
  * transformers' Gemma-2 default pattern).  No effect while cfg.sliding_window == 0 (the reference never slides). */
 int b2_set_layer_types(b2_engine* e, const int32_t* is_sliding, int n_layers);
@@ -174,6 +182,7 @@ typedef struct b2_stats {
   int64_t comm_calls;      /* tensor parallelism: NCCL collectives enqueued since the last reset */
   double comm_bytes;       /* payload bytes of those collectives on this rank */
   double comm_ms;          /* their device time, only while timing is on */
+  int64_t p2p_fused;       /* tensor parallelism: fused all-reduce + RMSNorm kernels over peer memory launched (host-side count) */
 } b2_stats;
 /* on = 1: record CUDA events around every GEMM / attention launch; on = k > 1: only on every k-th forward (the other
  * forwards take the plain launch path, so a timed region mostly runs exactly what an untimed one runs); 0 = off */

@@ -27,7 +27,7 @@ class B2Stats(C.Structure):
     _fields_ = [("launches", C.c_int64), ("gemm_launches", C.c_int64), ("gemm_ms", C.c_double),
                 ("gemm_flops", C.c_double), ("attn_ms", C.c_double), ("attn_flops", C.c_double),
                 ("attn_launches", C.c_int64), ("timed_forwards", C.c_int64), ("comm_calls", C.c_int64),
-                ("comm_bytes", C.c_double), ("comm_ms", C.c_double)]
+                ("comm_bytes", C.c_double), ("comm_ms", C.c_double), ("p2p_fused", C.c_int64)]
 
 
 class B2ForwardArgs(C.Structure):
@@ -58,6 +58,8 @@ SYMBOLS = [
     ("b2_set_layer_types", _I, [_P, C.POINTER(C.c_int32), _I]),
     ("b2_tp_unique_id", _I, [_P]),
     ("b2_tp_init", _I, [_P, _P]),
+    ("b2_tp_ipc_handle", _I, [_P, _P]),
+    ("b2_tp_set_peers", _I, [_P, _P, _I]),
     ("b2_forward_host", _I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     ("b2_set_decode_graph", _I, [_P, _I]),
     ("b2_sample_min_p", _I, [_P, _P, _I, _I, _F, _P, _P, _P, _P]),

@@ -484,6 +484,121 @@ min_p_sample_kernel(const float* __restrict__ logits, int ld, int V, float p_bas
 }  // namespace b2
 
 namespace b2 {
+// ---------------------------------------------------------------------------------------------
+// Tensor-parallel decode: all-reduce + residual add + RMSNorm in ONE kernel over peer memory (NVLink P2P).
+// Every rank's row-parallel o_proj / down_proj GEMM leaves its fp32 partial planes in a buffer that the other ranks have
+// mapped (cudaIpc).  This kernel replaces ncclAllReduce + rmsnorm_row_kernel:
+//   1. cross-GPU barrier through flags in peer memory: block 0 tells every peer "my partials of this round are written"
+//      (st.release.sys into the peer's flag array), every block waits until all peers have said the same (ld.acquire.sys
+//      on its own flags); rounds count up, nothing is ever reset;
+//   2. x[row] += sum over ranks (rank order) of sum over split planes (plane order) -- peers' planes are read straight
+//      over NVLink with volatile loads; every rank adds the same numbers in the same order, so the replicas of x stay
+//      bit-identical;
+//   3. the usual RMSNorm of the row.
+// Two buffers ("sites": 0 after o_proj, 1 after down_proj) alternate, which is what makes overwriting a buffer safe: a
+// rank re-writes site 0 only after it has passed the site-1 barrier of the same layer, i.e. after every peer has entered
+// its own post-down_proj kernel and therefore finished reading site 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int TP_MAX_WORLD = 8;
+struct TpPeers {
+  const float* part[TP_MAX_WORLD];   // this site's partial planes of rank p (own buffer for p == rank)
+  unsigned* flags[TP_MAX_WORLD];     // rank p's flag array [2 sites][TP_MAX_WORLD]
+  int rank, world;
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+tp_allreduce_norm_row_kernel(float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ out_bf16, int ld_out,
+                             float* __restrict__ out_f32, int H, float eps, const TpPeers peers, int nsplit, size_t split_stride,
+                             unsigned* __restrict__ round_ctr, unsigned* __restrict__ done_ctr, int site) {
+  pdl_trigger();
+  pdl_wait();                                  // this rank's GEMM is complete: its partial planes are in this GPU's memory
+  __shared__ float red[8];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    const unsigned round = *reinterpret_cast<volatile unsigned*>(round_ctr + site) + 1;   // same value in every block (bumped by the last block out)
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < peers.world; ++p)
+        if (p != peers.rank) st_release_sys(peers.flags[p] + site * TP_MAX_WORLD + peers.rank, round);
+    }
+    for (int p = 0; p < peers.world; ++p) {
+      if (p == peers.rank) continue;
+      unsigned spins = 0;
+      while (ld_acquire_sys(peers.flags[peers.rank] + site * TP_MAX_WORLD + p) < round) {
+        __nanosleep(64);
+        if (++spins > (1u << 25)) {            // seconds: a peer never arrived -- fail loudly instead of hanging the GPU
+          printf("b2: tensor-parallel barrier timeout (rank %d waiting for rank %d, site %d, round %u)\n", peers.rank, p, site, round);
+          __trap();
+        }
+      }
+    }
+    red[0] = __uint_as_float(round);
+  }
+  __syncthreads();
+  const unsigned round = __float_as_uint(red[0]);
+  __syncthreads();
+  const int nv4 = H >> 2;
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H);
+  float4 v[3];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int idx = tid + i * 256;
+    if (idx < nv4) {
+      v[i] = xr[idx];
+      for (int p = 0; p < peers.world; ++p)
+        for (int s = 0; s < nsplit; ++s) {
+          const float4* src = reinterpret_cast<const float4*>(peers.part[p] + s * split_stride + static_cast<size_t>(row) * H) + idx;
+          const float4 a = (p == peers.rank) ? *src : ld_volatile_f4(src);
+          v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+        }
+      xr[idx] = v[i];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float rs = 1.0f / sqrtf(tot / static_cast<float>(H) + eps);
+  const float4* gr = reinterpret_cast<const float4*>(g);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int idx = tid + i * 256;
+    if (idx < nv4) {
+      const float4 gg = __ldg(gr + idx);
+      const float4 o = make_float4(v[i].x * rs * gg.x, v[i].y * rs * gg.y, v[i].z * rs * gg.z, v[i].w * rs * gg.w);
+      if (out_bf16)
+        *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * ld_out + idx * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * H)[idx] = o;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {                              // last block out publishes the round for the next use of this site
+    __threadfence();
+    if (atomicAdd(done_ctr + site, 1u) == gridDim.x - 1) {
+      done_ctr[site] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(round_ctr + site) = round;
+    }
+  }
+}
+
 // vocabulary-parallel lm_head (tensor parallelism): ncclAllGather leaves [world][rows][V_local]; the caller's logits are
 // [rows][world * V_local].  One float4 per thread, coalesced on both sides.
 __global__ void __launch_bounds__(256)

@@ -615,6 +615,14 @@ struct b2_engine {
   size_t tp_lg_elems = 0;
   int64_t comm_calls = 0;
   double comm_bytes = 0;
+  // peer-memory path of the tensor-parallel decode step (b2_tp_ipc_handle / b2_tp_set_peers): one IPC-shared buffer per
+  // rank = [2 sites][MAX_SPLIT][128][H] fp32 partial planes + flags; peers' buffers mapped with cudaIpcOpenMemHandle
+  float* p2p_buf = nullptr;
+  size_t p2p_site_floats = 0;
+  unsigned* p2p_ctr = nullptr;           // [0..1] round counters, [2..3] blocks-done counters (local)
+  void* p2p_peer[8] = {};                // mapped base pointers of the peers' buffers (nullptr for self)
+  bool p2p_ready = false;
+  int64_t p2p_fused = 0;                 // fused all-reduce+norm kernels launched since the last reset
   bf16* embed = nullptr;
   float* g_final = nullptr;
   bool embed_loaded = false, final_loaded = false;
@@ -872,6 +880,10 @@ extern "C" void b2_engine_destroy(b2_engine* e) {
   cudaFree(e->logits_ws);
   cudaFree(e->tp_lg); cudaFree(e->tp_gather);
   if (e->comm && nccl_api()) nccl_api()->CommDestroy(e->comm);
+  for (int p = 0; p < 8; ++p)
+    if (e->p2p_peer[p]) cudaIpcCloseMemHandle(e->p2p_peer[p]);
+  cudaFree(e->p2p_buf);
+  cudaFree(e->p2p_ctr);
   cudaFree(e->embed); cudaFree(e->g_final); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
   for (auto& L : e->layers) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd);
@@ -1234,12 +1246,30 @@ struct Fold {
   const float* src = nullptr;
   int n = 0;
   size_t stride = 0;
+  int tp_site = -1;      // >= 0: the planes live in the peer-mapped buffer of that site on EVERY rank: the norm kernel all-reduces
 };
 
 static int rmsnorm(b2_engine* e, cudaStream_t st, float* x, const float* g, bf16* ob, float* of, int M, Fold f = Fold()) {
   const int H = e->cfg.hidden_size, pf = e->cfg.precise ? 2 : 1;
   const int ld = pf * H, lo = e->cfg.precise ? H : 0;   // precise: [hi | lo] rows
   e->st.launches++;
+  if (f.tp_site >= 0) {   // tensor-parallel decode: all-reduce over peer memory + residual + norm in one kernel
+    if (M > 128 || lo) return fail(B2_ERR_STATE, "internal: peer-memory all-reduce is a few-row, non-precise path");
+    TpPeers pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.rank = e->tp_rank;
+    pr.world = e->tp_world;
+    const size_t flag_off = 2 * e->p2p_site_floats;
+    for (int p = 0; p < e->tp_world; ++p) {
+      float* base = p == e->tp_rank ? e->p2p_buf : static_cast<float*>(e->p2p_peer[p]);
+      pr.part[p] = base + static_cast<size_t>(f.tp_site) * e->p2p_site_floats;
+      pr.flags[p] = reinterpret_cast<unsigned*>(base + flag_off);
+    }
+    CK(launch_k(tp_allreduce_norm_row_kernel, dim3(M), dim3(256), 0, st, x, g, ob, ld, of, H, e->cfg.rms_norm_eps, pr, f.n, f.stride,
+                e->p2p_ctr, e->p2p_ctr + 2, f.tp_site));
+    e->p2p_fused++;
+    return B2_OK;
+  }
   if (M <= 128) {   // decode / tiny prompts: a CTA per row keeps every load of the row in flight
     CK(launch_k(rmsnorm_row_kernel, dim3(M), dim3(256), 0, st, x, g, ob, ld, lo, of, H, e->cfg.rms_norm_eps,
                 f.src, f.n, f.stride));
@@ -1313,7 +1343,7 @@ struct FwdArgs {
 //   few rows (decode)        split-K partial planes in e->part (all SMs stream weights)                  f = {part, ns, stride}
 //   tensor parallel          this rank's partial sum -> ncclAllReduce over the ranks                     f = {y or part, ...}
 //   Gemma-2                  y is needed on its own (post-norm before the residual add), never EPI_RESID f = {y or part, ...}
-static int row_parallel_proj(b2_engine* e, cudaStream_t st, const bf16* a, int K, const bf16* w, int M, bool skinny, Fold& f) {
+static int row_parallel_proj(b2_engine* e, cudaStream_t st, const bf16* a, int K, const bf16* w, int M, bool skinny, Fold& f, int site) {
   const b2_config& c = e->cfg;
   const int H = c.hidden_size;
   const bool tp = e->tp_world > 1;
@@ -1321,11 +1351,14 @@ static int row_parallel_proj(b2_engine* e, cudaStream_t st, const bf16* a, int K
   f = Fold();
   if (skinny) {
     const int sr = tp ? ((M + 31) / 32) * 32 : 128;      // tp: planes packed back to back so one all-reduce covers them
-    p.out = e->part; p.ldo = H; p.split_rows = sr;
+    const bool p2p = tp && e->p2p_ready && !c.gemma;     // Llama decode: the following norm kernel all-reduces over peer memory
+    float* planes = p2p ? e->p2p_buf + static_cast<size_t>(site) * e->p2p_site_floats : e->part;
+    p.out = planes; p.ldo = H; p.split_rows = sr;
     p.split_k = pick_split(H, K, 64);
     CKR(eng_gemm(e, st, 64, EPI_F32, a, K, w, p, 0, MAX_SPLIT * 128));
-    f.src = e->part; f.n = p.split_k; f.stride = static_cast<size_t>(sr) * H;
-    if (tp) CKR(tp_allreduce(e, st, e->part, static_cast<size_t>(p.split_k) * sr * H));
+    f.src = planes; f.n = p.split_k; f.stride = static_cast<size_t>(sr) * H;
+    if (p2p) f.tp_site = site;
+    else if (tp) CKR(tp_allreduce(e, st, e->part, static_cast<size_t>(p.split_k) * sr * H));
     return B2_OK;
   }
   if (!c.gemma && !tp) {
@@ -1506,7 +1539,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
       e->st.attn_launches++;
     }
     Fold f;
-    CKR(row_parallel_proj(e, st, e->att, e->q_cols, Ly.wo, M, skinny, f));                // attn . Wo^T
+    CKR(row_parallel_proj(e, st, e->att, e->q_cols, Ly.wo, M, skinny, f, 0));             // attn . Wo^T
     if (!c.gemma) {
       CKR(rmsnorm(e, st, e->x, Ly.g_post_attn, e->xn, nullptr, M, f));                     // x += ...; xn = norm(x)
     } else {   // Gemma-2: x += post_attention_norm(attn_out); xn = pre_feedforward_norm(x)  (gemma2_model.py:623-641)
@@ -1523,7 +1556,7 @@ static int run_layers(b2_engine* e, b2_cache* cache, cudaStream_t st, const FwdA
       const int bn_glu = (M <= 128 && (2 * I) / 128 <= e->n_sms) ? 128 : pick_bn(M, 2 * I, 0);
       CKR(eng_gemm(e, st, bn_glu, EPI_GLU, e->xn, H, Ly.wgu, p));                          // act(gate)*up
     }
-    CKR(row_parallel_proj(e, st, e->hb, I, Ly.wd, M, skinny, f));                          // h . Wd^T
+    CKR(row_parallel_proj(e, st, e->hb, I, Ly.wd, M, skinny, f, 1));                       // h . Wd^T
     if (!c.gemma) {
       pend = f;                  // folded into x by the next layer's input norm / the final norm
       if (hidden && pend.n) {    // hidden-state capture copies x at the top of the next layer: fold now
@@ -1724,6 +1757,41 @@ extern "C" int b2_tp_init(b2_engine* e, const void* id) {
   return B2_OK;
 }
 
+// Peer-memory path of the tensor-parallel decode step: every rank exports one buffer (b2_tp_ipc_handle), the caller
+// all-gathers the 64-byte handles, every rank maps its peers' buffers (b2_tp_set_peers).  From then on the all-reduces of
+// the few-row (decode) Llama path run inside tp_allreduce_norm_row_kernel over NVLink instead of through NCCL.
+extern "C" int b2_tp_ipc_handle(b2_engine* e, void* handle_out) {
+  if (!e || !handle_out) return fail(B2_ERR_ARG, "null argument");
+  if (e->tp_world <= 1) return fail(B2_ERR_ARG, "engine was created with tp_world <= 1");
+  static_assert(sizeof(cudaIpcMemHandle_t) == B2_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  CK(cudaSetDevice(e->device));
+  if (!e->p2p_buf) {
+    e->p2p_site_floats = static_cast<size_t>(MAX_SPLIT) * 128 * e->cfg.hidden_size;
+    const size_t bytes = 2 * e->p2p_site_floats * 4 + 4096;                 // planes of both sites + flags
+    CK(cudaMalloc(&e->p2p_buf, bytes));
+    CK(cudaMemset(e->p2p_buf, 0, bytes));
+    CK(cudaMalloc(&e->p2p_ctr, 16));
+    CK(cudaMemset(e->p2p_ctr, 0, 16));
+    CK(cudaDeviceSynchronize());
+  }
+  CK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle_out), e->p2p_buf));
+  return B2_OK;
+}
+extern "C" int b2_tp_set_peers(b2_engine* e, const void* handles, int n_handles) {
+  if (!e || !handles) return fail(B2_ERR_ARG, "null argument");
+  if (n_handles != e->tp_world || e->tp_world > TP_MAX_WORLD) return fail(B2_ERR_ARG, "expected %d handles (tp_world <= %d)", e->tp_world, TP_MAX_WORLD);
+  if (!e->p2p_buf) return fail(B2_ERR_STATE, "b2_tp_ipc_handle must be called first");
+  CK(cudaSetDevice(e->device));
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int p = 0; p < e->tp_world; ++p) {
+    if (p == e->tp_rank || e->p2p_peer[p]) continue;
+    CK(cudaIpcOpenMemHandle(&e->p2p_peer[p], h[p], cudaIpcMemLazyEnablePeerAccess));
+  }
+  e->p2p_ready = true;
+  for (auto it = e->graphs.begin(); it != e->graphs.end();) { auto cur = it++; drop_graph(e, cur); }
+  return B2_OK;
+}
+
 extern "C" int b2_set_layer_types(b2_engine* e, const int32_t* is_sliding, int n) {
   if (!e || !is_sliding) return fail(B2_ERR_ARG, "null argument");
   if (n != e->cfg.num_hidden_layers) return fail(B2_ERR_ARG, "layer_types has %d entries, the model has %d layers", n, e->cfg.num_hidden_layers);
@@ -1821,6 +1889,7 @@ extern "C" int b2_reset_stats(b2_engine* e) {
   e->st.forwards = e->st.timed_forwards = 0;
   e->comm_calls = 0;
   e->comm_bytes = 0;
+  e->p2p_fused = 0;
   return B2_OK;
 }
 extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
@@ -1832,6 +1901,7 @@ extern "C" int b2_get_stats(b2_engine* e, b2_stats* out) {
   out->attn_launches = e->st.attn_launches;
   out->timed_forwards = e->st.timed_forwards;
   out->comm_calls = e->comm_calls;
+  out->p2p_fused = e->p2p_fused;
   out->comm_bytes = e->comm_bytes;
   if (!e->st.used.empty()) {
     CK(cudaDeviceSynchronize());

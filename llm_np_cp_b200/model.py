@@ -238,6 +238,12 @@ class _CausalLM:
             src = dist.get_global_rank(tp_group, 0) if tp_group is not None else 0
             dist.broadcast_object_list(box, src=src, group=tp_group, device=self.device)
             check(L.b2_tp_init(self._h, box[0]))      # ncclCommInitRank: collective over the group
+            if not os.environ.get("B2_TP_NO_P2P"):    # peer-memory all-reduce for the decode step (NVLink P2P, cudaIpc)
+                hbuf = (C.c_uint8 * 64)()
+                check(L.b2_tp_ipc_handle(self._h, hbuf))
+                gathered = [None] * self.tp_world
+                dist.all_gather_object(gathered, bytes(hbuf), group=tp_group)
+                check(L.b2_tp_set_peers(self._h, b"".join(gathered), self.tp_world))
         self._graph_on = False
         self._step_logits, self._step_ids = {}, {}
         src = weights_dict if weights_dict is not None else weights

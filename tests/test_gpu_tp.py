@@ -48,6 +48,7 @@ for fam in ("llama", "gemma2"):
         steps.append(tp(ids[:, t:t + 1], use_cache=True, kv_cache=cache, output_hidden_states=False, logits_mode=2)[1])
     torch.cuda.synchronize()
     st = tp.stats()
+    p2p = int(st["p2p_fused"])
     if rank == 0:
         one = cls(M.AttributeDict(cfg), w, device=0, **kw)
         _, lg1, _, hs1, _ = one(ids, use_cache=False)
@@ -56,7 +57,7 @@ for fam in ("llama", "gemma2"):
         for t in range(290, 300):
             s1.append(one(ids[:, t:t + 1], use_cache=True, kv_cache=c1, output_hidden_states=False, logits_mode=2)[1])
         res[fam] = dict(logits=rel(lg, lg1), hidden=max(rel(a, b) for a, b in zip(hs, hs1)),
-                        decode=max(rel(a, b) for a, b in zip(steps, s1)), comm_calls=int(st["comm_calls"]),
+                        decode=max(rel(a, b) for a, b in zip(steps, s1)), comm_calls=int(st["comm_calls"]), p2p_fused=p2p,
                         comm_bytes=float(st["comm_bytes"]), std=float(lg1.std()))
         del one
     del tp
@@ -80,6 +81,9 @@ def test_tensor_parallel_equals_single_gpu(tmp_path, world):
     res = json.load(open(out))
     for fam, v in res.items():
         print(f"[parity-tp] {fam} tp={world} vs 1 GPU: max_abs/std logits {v['logits']:.4g} hidden {v['hidden']:.4g} "
-              f"decode {v['decode']:.4g}; {v['comm_calls']} NCCL calls, {v['comm_bytes'] / 1e6:.2f} MB")
+              f"decode {v['decode']:.4g}; {v['comm_calls']} NCCL calls, {v['comm_bytes'] / 1e6:.2f} MB, "
+              f"{v['p2p_fused']} fused all-reduce+norm kernels over peer memory (host-side count, graph capture included)")
         assert v["logits"] <= 0.04 and v["hidden"] <= 0.04 and v["decode"] <= 0.04, (fam, v)
         assert v["comm_calls"] > 0
+        if fam == "llama":
+            assert v["p2p_fused"] > 0        # the Llama decode steps all-reduce inside the norm kernel, over NVLink P2P

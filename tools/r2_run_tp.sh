@@ -24,7 +24,9 @@ if [ "$N" = "2" ]; then
 echo "== 1 GPU prefill 3B S=8192 B=1 (same work on one GPU)"
 timeout 300 python bench.py --model 3b --seq 8192 --batch 1 --steps 4 --warmup 2 --no-precise --no-cpu-baseline --no-decode 2>/dev/null | tee gpurun_out/r2_tp_prefill_1gpu_ref.json | show
 fi
-echo "== TP=$N decode 1B B=64"
+echo "== TP=$N decode 1B B=64, NCCL all-reduce only (B2_TP_NO_P2P=1)"
+B2_TP_NO_P2P=1 timeout 240 bash -c "$(declare -f tr); N=$N; tr --tp $N --workload decode --steps 3 --warmup 1" 2>/dev/null | tee gpurun_out/r2_tp_decode_${N}_nccl.json | show
+echo "== TP=$N decode 1B B=64 (fused all-reduce + RMSNorm over peer memory)"
 timeout 240 bash -c "$(declare -f tr); N=$N; tr --tp $N --workload decode --steps 3 --warmup 1" 2>gpurun_out/r2_tp_decode_${N}.err | tee gpurun_out/r2_tp_decode_${N}.json | show
 if [ "$N" != "8" ]; then
 echo "== DP x$N prefill 1B (default line)"
