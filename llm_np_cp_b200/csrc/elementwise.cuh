@@ -491,7 +491,7 @@ namespace b2 {
 //   1. cross-GPU barrier through flags in peer memory: block 0 tells every peer "my partials of this round are written"
 //      (st.release.sys into the peer's flag array), every block waits until all peers have said the same (ld.acquire.sys
 //      on its own flags); rounds count up, nothing is ever reset;
-//   2. x[row] += sum over ranks (rank order) of sum over split planes (plane order) -- peers' planes are read straight
+//   2. x[row] += sum over split planes (plane order) of sum over ranks (rank order) -- peers' planes are read straight
 //      over NVLink with volatile loads; every rank adds the same numbers in the same order, so the replicas of x stay
 //      bit-identical;
 //   3. the usual RMSNorm of the row.
@@ -559,12 +559,20 @@ tp_allreduce_norm_row_kernel(float* __restrict__ x, const float* __restrict__ g,
     const int idx = tid + i * 256;
     if (idx < nv4) {
       v[i] = xr[idx];
-      for (int p = 0; p < peers.world; ++p)
-        for (int s = 0; s < nsplit; ++s) {
-          const float4* src = reinterpret_cast<const float4*>(peers.part[p] + s * split_stride + static_cast<size_t>(row) * H) + idx;
-          const float4 a = (p == peers.rank) ? *src : ld_volatile_f4(src);
-          v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
-        }
+      for (int s = 0; s < nsplit; ++s) {
+        // all ranks' loads of this plane are in flight together (one NVLink round trip, not `world` dependent ones);
+        // the sum runs in rank order afterwards -- the same order on every rank
+        float4 a[TP_MAX_WORLD];
+#pragma unroll
+        for (int p = 0; p < TP_MAX_WORLD; ++p)
+          if (p < peers.world) {
+            const float4* src = reinterpret_cast<const float4*>(peers.part[p] + s * split_stride + static_cast<size_t>(row) * H) + idx;
+            a[p] = (p == peers.rank) ? *src : ld_volatile_f4(src);
+          }
+#pragma unroll
+        for (int p = 0; p < TP_MAX_WORLD; ++p)
+          if (p < peers.world) { v[i].x += a[p].x; v[i].y += a[p].y; v[i].z += a[p].z; v[i].w += a[p].w; }
+      }
       xr[idx] = v[i];
       ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     }

@@ -68,10 +68,11 @@ dist.destroy_process_group()
 """
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_tensor_parallel_equals_single_gpu(tmp_path, world):
     import json
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs (gpurun --gpus {world})")
     script, out = tmp_path / "tp_worker.py", tmp_path / "tp.json"
     script.write_text(WORKER)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
