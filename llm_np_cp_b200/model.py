@@ -238,7 +238,12 @@ class _CausalLM:
             src = dist.get_global_rank(tp_group, 0) if tp_group is not None else 0
             dist.broadcast_object_list(box, src=src, group=tp_group, device=self.device)
             check(L.b2_tp_init(self._h, box[0]))      # ncclCommInitRank: collective over the group
-            if not os.environ.get("B2_TP_NO_P2P"):    # peer-memory all-reduce for the decode step (NVLink P2P, cudaIpc)
+            # Peer-memory all-reduce fused into the norm kernel for the decode step (NVLink P2P, cudaIpc).  Measured on B200
+            # (decode, B=64): 1.32 vs 1.51 ms per token step at TP=2, 1.50 vs 1.56 at TP=4; at TP=8 every rank pulls seven
+            # peers' planes and NCCL's in-switch (NVLS) reduction wins (1.77 ms), so the default stops at 4 ranks.
+            # B2_TP_P2P=1 forces it on, B2_TP_NO_P2P=1 off.
+            use_p2p = (self.tp_world <= 4 or os.environ.get("B2_TP_P2P")) and not os.environ.get("B2_TP_NO_P2P")
+            if use_p2p:
                 hbuf = (C.c_uint8 * 64)()
                 check(L.b2_tp_ipc_handle(self._h, hbuf))
                 gathered = [None] * self.tp_world
