@@ -26,6 +26,16 @@ def test_config_struct_matches_header():
     assert fields == [f for f, _ in _lib.B2Config._fields_]
 
 
+@pytest.mark.parametrize("struct,cls", [("b2_forward_args", "B2ForwardArgs"), ("b2_stats", "B2Stats")])
+def test_other_structs_match_header(struct, cls):
+    """Field order of every struct that crosses the ABI: header declaration == ctypes mirror."""
+    hdr = open(os.path.join(ROOT, "include", "b200fwd.h")).read()
+    body = hdr[hdr.index(f"typedef struct {struct} {{"):hdr.index(f"}} {struct};")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b\*?\s*([a-zA-Z_][a-zA-Z0-9_]*)\s*[,;]", body)
+    assert fields == [f for f, _ in getattr(_lib, cls)._fields_]
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():

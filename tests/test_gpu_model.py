@@ -137,6 +137,24 @@ def test_paged_cache_is_bit_identical_to_dense(family):
         model(ids[:, :4], use_cache=True, kv_cache=bad, output_hidden_states=False)
 
 
+def test_decode_step_with_caller_position_ids():
+    """A one-token step on a cache with a caller-supplied position (llama3.2_model_numpy.py:657): RoPE reads the table at
+    that position while K/V are appended at the cache length -- through the 5-kernel decode path -- vs the oracle."""
+    cfg = O.llama_config("tiny")
+    w = O.synth_weights(cfg, 9, 0.08, 0.1)
+    wn = O.to_numpy_f32(w)
+    model = M.LlamaForCausalLM(M.AttributeDict(cfg), w)
+    ids = np.random.default_rng(13).integers(0, cfg.vocab_size, (3, 7))
+    oc, cache = O.KVCache(), M.KVCache(max_tokens=32)
+    O.forward(cfg, wn, ids[:, :6], oc)
+    model(ids[:, :6], use_cache=True, kv_cache=cache, output_hidden_states=False)
+    want = O.forward(cfg, wn, ids[:, 6:7], oc, position_ids=[[20]]).logits
+    _, got, _, _, _ = model(ids[:, 6:7], position_ids=[[20]], use_cache=True, kv_cache=cache, output_hidden_states=False)
+    check_close(got.cpu().numpy(), want, "decode step with position_ids=[[20]] on a 6-token cache")
+    plain = O.forward(cfg, wn, ids[:, 6:7], O.KVCache()).logits      # sanity: the position matters
+    assert cache.num_items() == 7 and np.abs(want - plain).max() > 1e-2
+
+
 def test_decode_graph_matches_plain():
     meta, arr = load_golden("llama_tiny_decode")
     cfg, w, model = build(meta)
@@ -382,12 +400,13 @@ def test_precise_prefill_within_1e2_of_reference(name):
         assert np.abs(h.cpu().numpy() - arr["hidden"][i]).max() <= PRECISE_TOL
 
 
+@pytest.mark.parametrize("paged", [False, True])
 @pytest.mark.parametrize("name", ["llama_tiny_decode", "gemma2_tiny_decode"])
-def test_precise_decode_within_1e2_of_reference(name):
+def test_precise_decode_within_1e2_of_reference(name, paged):
     meta, arr = load_golden(name)
     cfg, w, model = build(meta, precise=True)
     S, dec = meta["S"], meta["decode_steps"]
-    cache = M.KVCache(max_tokens=64)
+    cache = M.KVCache(max_tokens=256, paged=True) if paged else M.KVCache(max_tokens=64)   # paged: hi and lo planes are page pools
     _, logits, _, _, _ = model(arr["ids"][:, :S], use_cache=True, kv_cache=cache)
     assert np.abs(logits.cpu().numpy() - arr["logits"]).max() <= PRECISE_TOL
     for i in range(dec):
