@@ -2,11 +2,15 @@
 """bench.py -- BASELINE.json's metric: prefill tokens/s, Llama-3.2-1B shapes, bf16, seq=2048.
 
   python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU under torchrun)
-  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (NumPy port) on host cores
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU module (oracle/_ref build) on host cores
+  python bench.py --workload decode [--prompt P]           # config #5 as the headline line
+  torchrun --nproc-per-node N bench.py --gpus N --tp N ... # optional tensor parallelism: one batch over N GPUs
 
 A "step" is one forward of B sequences x 2048 synthetic tokens per GPU producing the full [B,S,V] fp32
 logits (what the reference's model(ids) returns).  Batches shard across GPUs with no collective (weak
-scaling).  One JSON line on stdout (rank 0).
+scaling).  One JSON line on stdout (rank 0); besides the contract keys it carries "decode" (a config-#5 rollout:
+BASELINE's metric ends "...; decode tok/s"), "precise" (the cost of the parity mode, labelled), "roofline",
+"cpu_baseline" and "clocks".
 """
 import os
 
