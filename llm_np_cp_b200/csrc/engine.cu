@@ -1144,6 +1144,7 @@ static int cache_ensure_pages(b2_cache* c, int tokens, cudaStream_t st) {
     if (nn > full) nn = full;
     const size_t new_plane = static_cast<size_t>(nn) * e->nkv * c->page * e->cfg.head_dim;
     if (c->pf == 2 && new_plane > 0x7fffffffull) return fail(B2_ERR_ARG, "precise-mode paged cache cannot grow to %lld pages", nn);
+    if (new_plane / e->cfg.head_dim > 0x7fffffffull) return fail(B2_ERR_ARG, "paged cache cannot grow to %lld pages (tensor-map row range)", nn);
     const int nplanes = e->cfg.num_hidden_layers * 2 * c->pf;
     bf16* nkv = nullptr;
     CK(cudaStreamSynchronize(st));
