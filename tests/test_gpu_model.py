@@ -341,6 +341,29 @@ def test_decode_graph_survives_cache_recreation():
     assert np.array_equal(torch.stack(outs).cpu().numpy(), a)
 
 
+def test_llama_1b_s128_vs_reference_golden():
+    """Llama-3.2-1B shapes, 128 tokens, all 16 layers, against outputs of the reference ITSELF (not the oracle): the mid-size
+    point between config #1 (16 tokens) and the oracle-checked benchmarked shapes.  16 M logits are compared, so the
+    maximum uses the large-sample tolerance of tests/test_gpu_baseline_shapes.py (0.16 std); the mean keeps 0.018."""
+    meta, arr = load_golden("llama_1b_s128")
+    cfg, w, model = build(meta)
+    _, logits, _, hs, _ = model(arr["ids"], use_cache=False)
+    lg = logits.cpu().numpy().astype(np.float64)
+    std = arr["logits_stats"][1]
+    for what, got, want in (("sub-sampled columns", lg[:, :, ::61], arr["logits_sub"]), ("last position", lg[:, -1, :], arr["logits_last"])):
+        d = np.abs(got - want)
+        print(f"[parity] 1B S=128 logits ({what}): max_abs={d.max():.4g} mean_abs={d.mean():.4g} ref_std={std:.4g} "
+              f"max/std={d.max() / std:.4g} mean/std={d.mean() / std:.4g}")
+        assert d.max() <= 0.16 * std and d.mean() <= MEAN_REL * std
+    agree = (lg.argmax(-1) == arr["argmax"]).mean()
+    print(f"[parity] 1B S=128 argmax agreement {agree:.3f}")
+    assert agree >= 0.9
+    hid = torch.stack(hs).cpu().numpy()[:, :, :, ::8]
+    for i in range(hid.shape[0]):
+        d = np.abs(hid[i] - arr["hidden_sub"][i])
+        assert d.max() <= 0.1 * arr["hidden_sub"][i].std() + 1e-3, (i, d.max())
+
+
 def test_gemma2_hf_flags_vs_oracle_extras():
     """Sliding window + attention soft-cap + query_pre_attn_scalar (absent from the reference; semantics
     of transformers' modeling_gemma2, restated in the oracle's Extras)."""
